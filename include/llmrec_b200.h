@@ -1,0 +1,184 @@
+/*
+ * llmrec_b200 -- C ABI of the B200 (sm_100a) kernels behind the LLMRec training-and-eval hot path.
+ *
+ * Boundary contract: the reference has no FFI layer -- its boundary is the
+ * Python API (MM_Model.forward, Trainer.bpr_loss/prune_loss, AdamW.step, test_torch).  These entry
+ * points are what a ctypes/cffi binding of that API binds: plain device pointers, sizes and a
+ * cudaStream_t.  No torch types.  Conventions:
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - all matrices are row-major fp32 with an explicit leading dimension (elements);
+ *   - index arrays are int32 (CSR rowptr/col; nnz < 2^31) unless stated;
+ *   - nothing is allocated, nothing synchronises the host; work is enqueued on `stream`;
+ *   - return 0 on success, non-zero on error; llmrec_last_error() gives the message
+ *     (the reference's only error convention is Python exceptions / sys.exit on NaN, main.py:287-289).
+ * Reference citations are file:line into HKUDS/LLMRec @ 169f3614.
+ */
+#ifndef LLMREC_B200_H
+#define LLMREC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* llmrec_stream_t; /* cudaStream_t */
+
+#define LLMREC_ABI_VERSION 1
+#define LLMREC_MAX_SEG 16
+
+int llmrec_abi_version(void);
+const char* llmrec_last_error(void);
+/* 1 when the running device is sm_100 (B200); kernels refuse to launch otherwise. */
+int llmrec_device_ok(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Propagation SpMM.  Replaces torch.sparse.mm / torch.mm(COO, dense) at Models.py:57-61,152-183
+ * (20 calls per forward) and their autograd transposes.
+ *
+ *   Y_s[r,:] (+)= epi( rs[r] * sum_{e in row r} v[e] * cs[col[e]] * X_s[col[e],:] )     s = 0..nseg-1
+ *
+ * One launch propagates `nseg` dense operands that share the sparsity pattern (the image / text /
+ * 5 attribute / profile / ID operands of one graph direction), reading the index stream once.
+ * vals, row_scale, col_scale may each be NULL (= 1).  The Trainer's graphs are binary patterns with
+ * rs = (deg+1e-8)^-1/2 (main.py:114-126), so vals == NULL there.
+ * seg flags: bit0 = row softmax over the d columns after scaling (Models.py:174-175); the optional
+ * addend Z is added after the epilogue (used by the backward chain: g_out = g_direct + A^T g).
+ * Optional row tiling (rows longer than tile_nnz are split over several warps and reduced by a
+ * deterministic second pass): pass NULL for one warp per row.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* X;   /* gathered operand  [n_cols x d], leading dimension ldx */
+  float* Y;         /* output            [n_rows x d], ldy */
+  const float* Z;   /* optional addend   [n_rows x d], ldz: Y = epi(...) + Z  (Z == Y accumulates in place) */
+  int64_t ldx;
+  int64_t ldy;
+  int64_t ldz;
+  int32_t flags;    /* LLMREC_SPMM_SOFTMAX */
+  int32_t _pad;
+} llmrec_spmm_seg;
+
+typedef struct {
+  const int32_t* tile_row;    /* [n_tiles] row of each tile; tiles of split rows are numbered first */
+  const int32_t* tile_beg;    /* [n_tiles] first nnz of the tile; end = min(beg+tile_nnz, row end) */
+  const int32_t* split_row;   /* [n_split] rows owning more than one tile */
+  const int32_t* split_first; /* [n_split+1] first tile of each split row (its tiles are consecutive) */
+  float* scratch;             /* [n_split_tiles * nseg * d] partial sums */
+  int32_t n_tiles, tile_nnz, n_split, n_split_tiles;
+} llmrec_spmm_tiling;
+
+#define LLMREC_SPMM_SOFTMAX 1
+
+int llmrec_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, const float* vals,
+                        const float* row_scale, const float* col_scale,
+                        int32_t n_rows, int32_t n_cols, int32_t d,
+                        const llmrec_spmm_seg* segs_host, int32_t nseg,
+                        const llmrec_spmm_tiling* tiling_host, llmrec_stream_t stream);
+
+/* Row softmax Y = softmax(X, dim=-1) and its backward dX = S*(dS - sum(dS*S)) (Models.py:174-175). */
+int llmrec_row_softmax_f32(const float* X, int64_t ldx, float* Y, int64_t ldy, int64_t n, int32_t d, llmrec_stream_t stream);
+int llmrec_row_softmax_bwd_f32(const float* S, int64_t lds, const float* dS, int64_t ldds, float* dX, int64_t lddx,
+                               int64_t n, int32_t d, llmrec_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Side-feature projection  Y = X W^T + b   (nn.Linear at Models.py:145-150; 8 per forward) and its
+ * weight gradient dW = dY^T X, db = colsum(dY) (autograd of the same; features are constants so
+ * there is no dX).  X:[n x k] ldx, W:[d x k] (nn.Linear layout), Y:[n x d] ldy.
+ * mode: 0 = tcgen05 3xTF32 (fp32-accurate, default), 1 = tcgen05 1xTF32, 2 = exact fp32 SIMT.
+ * --------------------------------------------------------------------------------------------- */
+int llmrec_proj_fwd_f32(const float* X, int64_t ldx, const float* W, const float* bias,
+                        float* Y, int64_t ldy, int64_t n, int32_t k, int32_t d, int32_t mode,
+                        llmrec_stream_t stream);
+int llmrec_proj_wgrad_f32(const float* X, int64_t ldx, const float* dY, int64_t lddy,
+                          float* dW, float* db, int64_t n, int32_t k, int32_t d, int32_t accumulate,
+                          int32_t mode, float* scratch, int64_t scratch_elems, llmrec_stream_t stream);
+/* scratch elements needed by llmrec_proj_wgrad_f32 for this shape/mode */
+int64_t llmrec_proj_wgrad_scratch(int64_t n, int32_t k, int32_t d, int32_t mode);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fusion (Models.py:185-197):  out = mean(layer_0..layer_{L}) + sum_t coef[t] * x_t / max(||x_t||_2, 1e-12)
+ * and its backward: d layer_l = g/(L+1) (written once to d_layer, may be NULL);
+ * d x_t (+)= coef[t] * (g - y_t (y_t . g)) / max(||x_t||,1e-12),  y_t = x_t/max(||x_t||,1e-12).
+ * Pointer tables are HOST arrays (copied into the launch parameters).
+ * --------------------------------------------------------------------------------------------- */
+/* rows: optional int32 device list of row ids to process (NULL = rows 0..n-1; n = list length otherwise). */
+int llmrec_fuse_fwd_f32(const float* const* layers_host, const int64_t* ld_layers_host, int32_t n_layers,
+                        const float* const* sides_host, const int64_t* ld_sides_host, const float* coef_host,
+                        int32_t n_sides, float* out, int64_t ldo, const int32_t* rows, int64_t n, int32_t d,
+                        llmrec_stream_t stream);
+int llmrec_fuse_bwd_f32(const float* g, int64_t ldg, int32_t n_layers, float* d_layer, int64_t lddl,
+                        const float* const* sides_host, const int64_t* ld_sides_host, const float* coef_host,
+                        float* const* d_sides_host, const int64_t* ld_dsides_host, int32_t n_sides,
+                        int32_t accumulate, const int32_t* rows, int64_t n, int32_t d, llmrec_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * BPR + prune heads (main.py:330-342 bpr_loss, :158-165 prune_loss, :232-254 the 8 heads).
+ * For head h with user matrix XU_h and item matrix XI_h (row-major, ld):
+ *   x_b   = <XU[u_b], XI[p_b]> - <XU[u_b], XI[n_b]>;  maxi_b = logsigmoid(x_b + 1e-8)
+ *   keep  = the int((1-drop_rate)*B) smallest maxi (ties -> lower b);  mf_h = -mean(maxi[keep])
+ *   emb_h = regs0/batch_size * sum_{t in u,p,n} 1/(2*sum||row_t||^2 + 1e-8)
+ * loss += w_mf[h]*mf_h + w_emb[h]*emb_h.  Gradients w.r.t. the gathered rows are scatter-added
+ * (atomicAdd) into GU_h / GI_h (same shapes as XU_h / XI_h; NULL = skip that head's grads).
+ * out_host-visible results live in `out` (device, 4 floats per head: mf, emb, kept, _) .
+ * idx are int32 device arrays of length B.  `n_keep` = int((1-drop_rate)*B) computed by the caller
+ * in double arithmetic like the reference (main.py:161-162).
+ * --------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* XU; const float* XI;
+  float* GU; float* GI;
+  int64_t ldxu, ldxi, ldgu, ldgi;
+  float w_mf, w_emb;
+} llmrec_bpr_head;
+
+int llmrec_bpr_heads_f32(const llmrec_bpr_head* heads_host, int32_t n_heads,
+                         const int32_t* users, const int32_t* pos, const int32_t* neg, int32_t B,
+                         int32_t n_keep, float regs0_over_bs, int32_t d,
+                         float* out /* [n_heads*4] */, float* loss_accum /* [1], += */,
+                         float* work /* llmrec_bpr_work_elems() floats, zeroed once */, llmrec_stream_t stream);
+int64_t llmrec_bpr_work_elems(int32_t n_heads, int32_t B);
+
+/* feat_reg_loss_calculation (main.py:151-156): loss += c * 0.5*sum(X^2) ; G = (accumulate? G:0) + c*X.
+ * G may be NULL (loss only). */
+int llmrec_sqnorm_grad_f32(const float* X, int64_t ldx, float* G, int64_t ldg, int64_t n, int32_t d,
+                           float c, int32_t accumulate, float* loss_accum, float* partial /* >= 1024 floats */,
+                           llmrec_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dense AdamW over a list of tensors (torch.optim.AdamW defaults at main.py:100-104,278:
+ * decoupled weight decay, bias correction).  `state` is a device block of 4 doubles
+ * {step, lr/bc1, sqrt(bc2), _}; llmrec_adamw_advance increments step and recomputes the scalars
+ * on device (CUDA-graph friendly).  Tensor tables are HOST arrays.
+ * --------------------------------------------------------------------------------------------- */
+int llmrec_adamw_advance(double* state, double lr, double beta1, double beta2, llmrec_stream_t stream);
+int llmrec_adamw_step_f32(float* const* p_host, const float* const* g_host, float* const* m_host, float* const* v_host,
+                          const int64_t* numel_host, int32_t n_tensors, const double* state,
+                          float lr, float beta1, float beta2, float eps, float weight_decay,
+                          llmrec_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Full-catalog scoring + top-K (utility/batch_test.py:149-152 scores, :21-36,100-102 ranking).
+ *   score[b,i] = <U[users[b]], I[i]>;  train items of the user are excluded; top-K by score,
+ *   ties -> lowest item id (heapq.nlargest over ascending candidates).
+ * mask CSR: mask_rowptr[int64? no: int32][n_users_total+1], mask_col sorted or not.  users = int32[b].
+ * out_idx int32 [b x K], out_val fp32 [b x K] (may be NULL).  K <= 64.
+ * mode: 0 = tcgen05 3xTF32 + fused select, 2 = exact fp32 SIMT.
+ * --------------------------------------------------------------------------------------------- */
+int llmrec_score_topk_f32(const float* U, int64_t ldu, const float* I, int64_t ldi,
+                          const int32_t* users, int32_t n_batch, int32_t n_items, int32_t d,
+                          const int32_t* mask_rowptr, const int32_t* mask_col,
+                          int32_t K, int32_t* out_idx, float* out_val, int32_t mode,
+                          float* scratch, int64_t scratch_elems, llmrec_stream_t stream);
+int64_t llmrec_score_topk_scratch(int32_t n_batch, int32_t n_items, int32_t d, int32_t K, int32_t mode);
+
+/* hits[b,j] = 1 if out_idx[b,j] in truth row of users[b] (test_set membership, batch_test.py:30-34). */
+int llmrec_topk_hits(const int32_t* idx, int32_t n_batch, int32_t K, const int32_t* users,
+                     const int32_t* truth_rowptr, const int32_t* truth_col, uint8_t* hits,
+                     llmrec_stream_t stream);
+
+/* small utilities used by the host mirror */
+int llmrec_fill_f32(float* p, int64_t n, float v, llmrec_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LLMREC_B200_H */

@@ -1,0 +1,228 @@
+"""The fused hot path: forward, losses, backward and AdamW of one LLMRec training step,
+scheduled by hand over the sm_100a kernels (no autograd, no host synchronisation).
+
+Follows (reference file:line):  MM_Model.forward  Models.py:127-199 ; bpr_loss / prune_loss /
+feat_reg / loss assembly  main.py:330-342,158-165,151-156,273 ; AdamW  main.py:100-104,278.
+Default flags only (mask off, dropout p = 0) -- the mask / MAE branch is out of scope.
+
+HBM layout (fp32, row-major):
+  Pi  [ni x S*d]  side-feature projections, column blocks  img | txt | att_0..att_4      (S = 2 + #keys)
+  Fu  [nu x S*d]  ui . Pi      (img_u | txt_u | att_u)        Fi [ni x S*d]  iu . Fu  (img_i | txt_i | att_i)
+  P_usr [nu x d], prof_i [ni x d] = iu . P_usr, prof_u [nu x d] = ui . prof_i
+  Ul[l] [nu x d], Il[l] [ni x d]  ID layers (l = 0 is the embedding table itself)
+  U [nu x d], I [ni x d]          fused outputs
+Every operand that shares a sparsity pattern rides in ONE SpMM launch (segments), so the reference's
+20 forward SpMMs are 2L launches (4 at L = 2) and the 20 backward ones 2L + 1.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from . import ops
+
+
+@dataclass
+class HotPathConfig:
+    embed_size: int = 64
+    n_layers: int = 2                 # len(weight_size)
+    model_cat_rate: float = 0.02
+    user_cat_rate: float = 2.8
+    item_cat_rate: float = 0.005
+    aug_mf_rate: float = 0.012
+    mm_mf_rate: float = 1e-4
+    prune_loss_drop_rate: float = 0.71
+    feat_reg_decay: float = 1e-5
+    regs0: float = 1e-5
+    batch_size: int = 1024
+    proj_mode: int = 0                # ops.PROJ_MODE
+
+
+PARAM_ORDER = ("image_trans.weight", "image_trans.bias", "text_trans.weight", "text_trans.bias",
+               "user_trans.weight", "user_trans.bias", "item_trans.weight", "item_trans.bias",
+               "user_id_embedding.weight", "item_id_embedding.weight")
+
+
+class HotPath:
+    """params: dict name -> fp32 CUDA tensor (the live parameter storage, updated in place).
+    feats: None (ID-only, the large synthetic config) or dict(image, text, user, item={key: tensor})."""
+
+    def __init__(self, operators, params, feats, cfg: HotPathConfig):
+        self.ui, self.iu, self.uiT, self.iuT = operators
+        self.cfg = cfg
+        self.p = params
+        self.feats = feats
+        d, L = cfg.embed_size, cfg.n_layers
+        self.E_u, self.E_i = params["user_id_embedding.weight"], params["item_id_embedding.weight"]
+        nu, ni = self.E_u.shape[0], self.E_i.shape[0]
+        self.nu, self.ni, self.d, self.L = nu, ni, d, L
+        dev = self.E_u.device
+        new = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+        self.has_feats = feats is not None
+        self.keys = list(feats["item"].keys()) if self.has_feats else []
+        S = self.S = (2 + len(self.keys)) if self.has_feats else 0
+        if self.has_feats:
+            self.Pi, self.Fu, self.Fi = new(ni, S * d), new(nu, S * d), new(ni, S * d)
+            self.P_usr, self.prof_i, self.prof_u = new(nu, d), new(ni, d), new(nu, d)
+            self.GPi, self.GFu, self.GFi = new(ni, S * d), new(nu, S * d), new(ni, S * d)
+            self.GP_usr, self.Gprof_i, self.Gprof_u = new(nu, d), new(ni, d), new(nu, d)
+            self.names = ["img", "txt"] + ["att:" + k for k in self.keys]
+        self.Ul = [self.E_u] + [new(nu, d) for _ in range(L)]
+        self.Il = [self.E_i] + [new(ni, d) for _ in range(L)]
+        self.U, self.I = new(nu, d), new(ni, d)
+        # gradients
+        self.gU, self.gI = new(nu, d), new(ni, d)
+        self.dIl = new(ni, d)
+        self.bufU, self.bufI, self.tmpI = new(nu, d), new(ni, d), new(ni, d)
+        self.grads = {k: torch.zeros_like(v) for k, v in params.items()}
+        self.dUl = self.grads["user_id_embedding.weight"]
+        self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.n_heads = (3 + len(self.keys)) if self.has_feats else 1
+        self.head_out = torch.zeros(self.n_heads * 4, dtype=torch.float32, device=dev)
+        self._bpr_work = None
+        self.opt = None
+
+    # ---- column-block views ------------------------------------------------------------------
+    def blk(self, buf, s):
+        d = self.d
+        return buf[:, s * d:(s + 1) * d]
+
+    def side_views(self):
+        """name -> tensor views in the order of the reference's return tuple (Models.py:199)."""
+        if not self.has_feats:
+            return {}
+        v = dict(img_i=self.blk(self.Fi, 0), txt_i=self.blk(self.Fi, 1), img_u=self.blk(self.Fu, 0), txt_u=self.blk(self.Fu, 1),
+                 p_usr=self.P_usr, prof_u=self.prof_u, prof_i=self.prof_i,
+                 att_i={k: self.blk(self.Fi, 2 + j) for j, k in enumerate(self.keys)},
+                 att_u={k: self.blk(self.Fu, 2 + j) for j, k in enumerate(self.keys)})
+        return v
+
+    # ---- forward -------------------------------------------------------------------------------
+    def forward(self):
+        d, L, S, m = self.d, self.L, self.S, self.cfg.proj_mode
+        p, f = self.p, self.feats
+        if self.has_feats:
+            ops.proj_fwd(f["image"], p["image_trans.weight"], p["image_trans.bias"], self.blk(self.Pi, 0), m)     # Models.py:145
+            ops.proj_fwd(f["text"], p["text_trans.weight"], p["text_trans.bias"], self.blk(self.Pi, 1), m)        # :146
+            for j, k in enumerate(self.keys):                                                                        # :148-150
+                ops.proj_fwd(f["item"][k], p["item_trans.weight"], p["item_trans.bias"], self.blk(self.Pi, 2 + j), m)
+            ops.proj_fwd(f["user"], p["user_trans.weight"], p["user_trans.bias"], self.P_usr, m)                  # :147
+        # step t even: ui (I_{t/2} -> U_{t/2+1});  t odd: iu (U_{(t+1)/2} -> I_{(t+1)/2}); softmax on the last layer
+        n_steps = max(2 * L, 3 if self.has_feats else 0)
+        for t in range(n_steps):
+            segs = []
+            if t % 2 == 0:
+                l = t // 2 + 1
+                if self.has_feats and t == 0:
+                    segs += [(self.blk(self.Pi, s), self.blk(self.Fu, s), None, False) for s in range(S)]                # :153,156,162
+                if self.has_feats and t == 2:
+                    segs.append((self.prof_i, self.prof_u, None, False))                                               # :167
+                if l <= L:
+                    segs.append((self.Il[l - 1], self.Ul[l], None, l == L))                                            # :174,178
+                self.ui.apply(segs)
+            else:
+                l = (t + 1) // 2
+                if self.has_feats and t == 1:
+                    segs += [(self.blk(self.Fu, s), self.blk(self.Fi, s), None, False) for s in range(S)]                # :154,157,163
+                    segs.append((self.P_usr, self.prof_i, None, False))                                                # :166
+                if l <= L:
+                    segs.append((self.Ul[l], self.Il[l], None, l == L))                                                # :175,180
+                self.iu.apply(segs)
+        c = self.cfg
+        if self.has_feats:
+            coefs = [c.model_cat_rate, c.model_cat_rate, c.user_cat_rate] + [c.item_cat_rate] * len(self.keys)
+            su = [self.blk(self.Fu, 0), self.blk(self.Fu, 1), self.prof_u] + [self.blk(self.Fu, 2 + j) for j in range(len(self.keys))]
+            si = [self.blk(self.Fi, 0), self.blk(self.Fi, 1), self.prof_i] + [self.blk(self.Fi, 2 + j) for j in range(len(self.keys))]
+        else:
+            coefs, su, si = [], [], []
+        ops.fuse_fwd(self.Ul, su, coefs, self.U)                                                                       # :185-197
+        ops.fuse_fwd(self.Il, si, coefs, self.I)
+        self._fuse_args = (coefs, su, si)
+        return self.U, self.I
+
+    # ---- backward: expects gU, gI and (GFu, GFi, Gprof_u, Gprof_i, GP_usr_direct) filled ---------------
+    def backward(self, gp_usr_direct=None, gpi_direct=None):
+        d, L, S, m = self.d, self.L, self.S, self.cfg.proj_mode
+        coefs, su, si = self._fuse_args
+        if self.has_feats:
+            dsu = [self.blk(self.GFu, 0), self.blk(self.GFu, 1), self.Gprof_u] + [self.blk(self.GFu, 2 + j) for j in range(len(self.keys))]
+            dsi = [self.blk(self.GFi, 0), self.blk(self.GFi, 1), self.Gprof_i] + [self.blk(self.GFi, 2 + j) for j in range(len(self.keys))]
+        else:
+            dsu, dsi = [], []
+        ops.fuse_bwd(self.gU, L + 1, self.dUl, su, coefs, dsu, True)
+        ops.fuse_bwd(self.gI, L + 1, self.dIl, si, coefs, dsi, True)
+        if self.has_feats:
+            # prof_u = ui . prof_i  ->  Gprof_i += ui^T Gprof_u
+            self.uiT.apply([(self.Gprof_u, self.Gprof_i, self.Gprof_i, False)])
+        gE_i = self.grads["item_id_embedding.weight"]
+        g_cur_I = self.dIl
+        for l in range(L, 0, -1):
+            # I_l = [softmax] iu . U_l
+            if l == L:
+                src = ops.row_softmax_bwd(self.Il[l], g_cur_I, out=self.tmpI)
+            else:
+                src = g_cur_I
+            segs = [(src, self.bufU, self.dUl, False)]
+            if self.has_feats and l == L:
+                segs += [(self.blk(self.GFi, s), self.blk(self.GFu, s), self.blk(self.GFu, s), False) for s in range(S)]
+                segs.append((self.Gprof_i, self.GP_usr, gp_usr_direct, False))
+            self.iuT.apply(segs)
+            # U_l = [softmax] ui . I_{l-1}
+            if l == L:
+                ops.row_softmax_bwd(self.Ul[l], self.bufU, out=self.bufU)
+            dst = gE_i if l == 1 else self.bufI
+            segs = [(self.bufU, dst, self.dIl, False)]
+            if self.has_feats and l == L:
+                segs += [(self.blk(self.GFu, s), self.blk(self.GPi, s), self.blk(gpi_direct, s) if gpi_direct is not None else None, False)
+                         for s in range(S)]
+            self.uiT.apply(segs)
+            g_cur_I = dst
+        if self.has_feats:
+            f, g = self.feats, self.grads
+            ops.proj_wgrad(f["image"], self.blk(self.GPi, 0), g["image_trans.weight"], g["image_trans.bias"], False, m)
+            ops.proj_wgrad(f["text"], self.blk(self.GPi, 1), g["text_trans.weight"], g["text_trans.bias"], False, m)
+            for j, k in enumerate(self.keys):
+                ops.proj_wgrad(f["item"][k], self.blk(self.GPi, 2 + j), g["item_trans.weight"], g["item_trans.bias"], j > 0, m)
+            ops.proj_wgrad(f["user"], self.GP_usr, g["user_trans.weight"], g["user_trans.bias"], False, m)
+        return self.grads
+
+    # ---- losses + their gradients w.r.t. the forward outputs ---------------------------------------------
+    def loss_and_output_grads(self, users, pos, neg):
+        """users/pos/neg: int32 CUDA tensors of equal length B' (sampled + augmented triplets)."""
+        c = self.cfg
+        B = int(users.numel())
+        n_keep = int((1 - c.prune_loss_drop_rate) * B)                     # main.py:161-162 (double arithmetic)
+        if self._bpr_work is None or self._bpr_work[0] != B:
+            self._bpr_work = (B, ops.bpr_work(self.n_heads, B, users.device))
+        self.loss.zero_()
+        self.gU.zero_(); self.gI.zero_()
+        heads = [(self.U, self.I, self.gU, self.gI, 1.0, 1.0)]                                                        # main.py:232-235
+        if self.has_feats:
+            self.GFu.zero_(); self.GFi.zero_(); self.Gprof_u.zero_(); self.Gprof_i.zero_()
+            creg = c.feat_reg_decay / self.ni                                                                          # main.py:151-156
+            d2 = 2 * self.d
+            ops.sqnorm_grad(self.Fu[:, :d2], self.GFu[:, :d2], creg, False, self.loss)
+            ops.sqnorm_grad(self.Fi[:, :d2], self.GFi[:, :d2], creg, False, self.loss)
+            heads.append((self.blk(self.Fu, 0), self.blk(self.Fi, 0), self.blk(self.GFu, 0), self.blk(self.GFi, 0), c.mm_mf_rate, 0.0))  # :238-241
+            heads.append((self.blk(self.Fu, 1), self.blk(self.Fi, 1), self.blk(self.GFu, 1), self.blk(self.GFi, 1), c.mm_mf_rate, 0.0))  # :242-246
+            for j in range(len(self.keys)):                                                                            # :248-254
+                heads.append((self.prof_u, self.blk(self.Fi, 2 + j), self.Gprof_u, self.blk(self.GFi, 2 + j), c.aug_mf_rate, 0.0))
+        ops.bpr_heads(heads, users, pos, neg, n_keep, c.regs0 / c.batch_size, self.head_out, self.loss, self._bpr_work[1])
+        return self.loss
+
+    def train_step(self, users, pos, neg):
+        """forward + losses + backward + AdamW; everything stays on the current stream."""
+        if self.opt is None:
+            raise RuntimeError("attach an optimizer with set_optimizer() first")
+        self.forward()
+        self.loss_and_output_grads(users, pos, neg)
+        self.backward()
+        self.opt.step([self.grads[k] for k in self._opt_names])
+        return self.loss
+
+    def set_optimizer(self, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01):
+        names = [k for k in PARAM_ORDER if k in self.p and (self.has_feats or k.endswith("embedding.weight"))]
+        self._opt_names = names
+        self.opt = ops.AdamW([self.p[k] for k in names], lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        return self.opt

@@ -1,0 +1,93 @@
+"""Device-resident bipartite interaction graph for the propagation kernels.
+
+The reference builds two fp32 COO tensors, ui = diag((deg_u+1e-8)^-1/2) R and
+iu = diag((deg_i+1e-8)^-1/2) R^T (main.py:84-91,114-134), and torch re-coalesces / converts them to
+CSR inside every torch.sparse.mm call.  Here the binary pattern R is stored ONCE as int32 CSR plus
+the CSR of its transpose and two fp32 scale vectors; the four operators the path needs are views:
+
+    ui   = diag(su) R          rows=users   pattern CSR(R)    row scale su
+    iu   = diag(si) R^T        rows=items   pattern CSR(R^T)  row scale si
+    ui^T = R^T diag(su)        rows=items   pattern CSR(R^T)  col scale su     (backward of ui)
+    iu^T = R diag(si)          rows=users   pattern CSR(R)    col scale si     (backward of iu)
+
+HBM layout: rowptr int32[n+1], col int32[nnz] (no value array), scales fp32[n].
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+from .ops import CsrOperator
+
+
+def inv_sqrt_degree(mat: sp.spmatrix) -> np.ndarray:
+    """(rowsum + 1e-8)^-1/2 in float64 with inf -> 0, as csr_norm does (main.py:114-118)."""
+    deg = np.asarray(mat.sum(1)).reshape(-1).astype(np.float64)
+    s = np.power(deg + 1e-8, -0.5)
+    s[np.isinf(s)] = 0.0
+    return s
+
+
+class BipartiteGraph:
+    def __init__(self, train_mat: sp.spmatrix, device, tile_nnz: int = 0):
+        R = sp.csr_matrix(train_mat)
+        R.sum_duplicates()
+        R.sort_indices()
+        Rt = sp.csr_matrix(R.T)
+        Rt.sort_indices()
+        self.n_users, self.n_items = R.shape
+        self.nnz = int(R.nnz)
+        if self.nnz >= 2 ** 31:
+            raise ValueError("graph too large for int32 CSR")
+        if not np.all(R.data == 1):
+            raise ValueError("BipartiteGraph expects a binary interaction matrix (use operators_from_coo for weighted graphs)")
+        dev = torch.device(device)
+        t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a.astype(dt))).to(dev)
+        self.rowptr_u, self.col_u = t(R.indptr, np.int32), t(R.indices, np.int32)
+        self.rowptr_i, self.col_i = t(Rt.indptr, np.int32), t(Rt.indices, np.int32)
+        self.su = t(inv_sqrt_degree(R), np.float32)
+        self.si = t(inv_sqrt_degree(Rt), np.float32)
+        nu, ni = self.n_users, self.n_items
+        self.ui = CsrOperator(self.rowptr_u, self.col_u, nu, ni, rs=self.su, tile_nnz=tile_nnz)
+        self.iu = CsrOperator(self.rowptr_i, self.col_i, ni, nu, rs=self.si, tile_nnz=tile_nnz)
+        self.uiT = CsrOperator(self.rowptr_i, self.col_i, ni, nu, cs=self.su, tile_nnz=tile_nnz)
+        self.iuT = CsrOperator(self.rowptr_u, self.col_u, nu, ni, cs=self.si, tile_nnz=tile_nnz)
+        self.device = dev
+
+    # the reference-facing COO tensors (what Trainer.ui_graph / iu_graph hold; main.py:128-134)
+    def coo_tensors(self):
+        def coo(rowptr, col, scale, shape):
+            rp = rowptr.to(torch.int64)
+            rows = torch.repeat_interleave(torch.arange(shape[0], device=self.device), rp[1:] - rp[:-1])
+            idx = torch.stack([rows, col.to(torch.int64)])
+            t = torch.sparse_coo_tensor(idx, scale[rows], shape)
+            return t
+        ui = coo(self.rowptr_u, self.col_u, self.su, (self.n_users, self.n_items))
+        iu = coo(self.rowptr_i, self.col_i, self.si, (self.n_items, self.n_users))
+        ui._llmrec_ops = (self.ui, self.uiT)
+        iu._llmrec_ops = (self.iu, self.iuT)
+        return ui, iu
+
+
+def operators_from_coo(A: torch.Tensor):
+    """(forward, backward) CsrOperators for an arbitrary fp32 sparse COO matrix (valued CSR path)."""
+    cached = getattr(A, "_llmrec_ops", None)
+    if cached is not None:
+        return cached
+
+    def csr(M):
+        M = M.coalesce()
+        idx, val = M.indices(), M.values().to(torch.float32).contiguous()
+        n_rows, n_cols = M.shape
+        counts = torch.bincount(idx[0], minlength=n_rows)
+        rowptr = torch.zeros(n_rows + 1, dtype=torch.int64, device=val.device)
+        rowptr[1:] = torch.cumsum(counts, 0)
+        return CsrOperator(rowptr.to(torch.int32), idx[1].to(torch.int32).contiguous(), n_rows, n_cols, vals=val)
+
+    ops = (csr(A), csr(A.t()))
+    try:
+        A._llmrec_ops = ops
+    except Exception:
+        pass
+    return ops

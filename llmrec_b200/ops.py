@@ -1,0 +1,270 @@
+"""Thin tensor-level wrappers over the C ABI (include/llmrec_b200.h).
+
+PyTorch supplies device memory and the current CUDA stream only; every op below is one or more
+launches of the hand-written sm_100a kernels.  2-D operands must be row-major views
+(stride(1) == 1); column slices of wider buffers are fine (the leading dimension is passed).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _native as N
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _mat(t: torch.Tensor, name="operand"):
+    if t.dim() != 2 or t.dtype != torch.float32 or not t.is_cuda or (t.shape[1] > 1 and t.stride(1) != 1):
+        raise ValueError(f"{name}: need a CUDA fp32 row-major 2-D tensor, got {tuple(t.shape)} {t.dtype} {t.device} strides {t.stride()}")
+    return t
+
+
+def _ld(t):
+    return int(t.stride(0)) if t.shape[0] > 1 else int(max(t.stride(0), t.shape[1]))
+
+
+def _i32(t, name="index"):
+    if t.dtype != torch.int32 or not t.is_cuda or not t.is_contiguous():
+        raise ValueError(f"{name}: need a contiguous CUDA int32 tensor")
+    return t
+
+
+class CsrOperator:
+    """One sparse operator  Y = diag(rs) . P(vals) . diag(cs) . X  over a CSR pattern P."""
+
+    def __init__(self, rowptr, col, n_rows, n_cols, vals=None, rs=None, cs=None, tile_nnz=0):
+        self.rowptr, self.col = _i32(rowptr, "rowptr"), _i32(col, "col")
+        self.vals, self.rs, self.cs = vals, rs, cs
+        self.n_rows, self.n_cols = int(n_rows), int(n_cols)
+        self.nnz = int(col.numel())
+        self._tiling = None
+        self._tiling_keep = None
+        if tile_nnz:
+            self.build_tiling(tile_nnz)
+
+    def build_tiling(self, tile_nnz: int):
+        """Split rows longer than tile_nnz into tiles (host-side, once per graph)."""
+        rp = self.rowptr.cpu().to(torch.int64)
+        deg = rp[1:] - rp[:-1]
+        if int(deg.max()) <= tile_nnz:
+            self._tiling = None
+            return
+        ntile = torch.clamp((deg + tile_nnz - 1) // tile_nnz, min=1)
+        split = torch.nonzero(ntile > 1).flatten()
+        whole = torch.nonzero(ntile <= 1).flatten()
+        rows, begs, first = [], [], [0]
+        for r in split.tolist():
+            k = int(ntile[r])
+            rows += [r] * k
+            begs += [int(rp[r]) + j * tile_nnz for j in range(k)]
+            first.append(first[-1] + k)
+        n_split_tiles = len(rows)
+        rows = torch.tensor(rows, dtype=torch.int64)
+        begs = torch.tensor(begs, dtype=torch.int64)
+        tile_row = torch.cat([rows, whole]).to(torch.int32)
+        tile_beg = torch.cat([begs, rp[whole]]).to(torch.int32)
+        dev = self.rowptr.device
+        keep = dict(tile_row=tile_row.to(dev), tile_beg=tile_beg.to(dev), split_row=split.to(torch.int32).to(dev),
+                    split_first=torch.tensor(first, dtype=torch.int32, device=dev), scratch=None,
+                    n_tiles=int(tile_row.numel()), tile_nnz=int(tile_nnz), n_split=int(split.numel()), n_split_tiles=n_split_tiles)
+        self._tiling_keep = keep
+        self._tiling = True
+
+    def _tiling_struct(self, width):
+        if not self._tiling:
+            return None
+        k = self._tiling_keep
+        need = k["n_split_tiles"] * width
+        if k["scratch"] is None or k["scratch"].numel() < need:
+            k["scratch"] = torch.empty(need, dtype=torch.float32, device=self.rowptr.device)
+        return N.SpmmTiling(_p(k["tile_row"]), _p(k["tile_beg"]), _p(k["split_row"]), _p(k["split_first"]), _p(k["scratch"]),
+                            k["n_tiles"], k["tile_nnz"], k["n_split"], k["n_split_tiles"])
+
+    def apply(self, segs):
+        """segs: list of (X, Y, Z_or_None, softmax: bool); all share d = X.shape[1]."""
+        if not segs:
+            return
+        d = int(segs[0][0].shape[1])
+        arr = (N.SpmmSeg * len(segs))()
+        for i, (X, Y, Z, sm) in enumerate(segs):
+            _mat(X, "spmm X"); _mat(Y, "spmm Y")
+            if X.shape[0] != self.n_cols or Y.shape[0] != self.n_rows or X.shape[1] != d or Y.shape[1] != d:
+                raise ValueError(f"spmm: shape mismatch X{tuple(X.shape)} Y{tuple(Y.shape)} for operator {self.n_rows}x{self.n_cols}")
+            arr[i] = N.SpmmSeg(_p(X), _p(Y), _p(Z) if Z is not None else None, _ld(X), _ld(Y), _ld(Z) if Z is not None else 0,
+                               N.SPMM_SOFTMAX if sm else 0, 0)
+        til = self._tiling_struct(d * min(len(segs), max(1, 1024 // d)))
+        N.check(N.lib().llmrec_spmm_csr_f32(_p(self.rowptr), _p(self.col), _p(self.vals), _p(self.rs), _p(self.cs),
+                                             self.n_rows, self.n_cols, d, arr, len(segs),
+                                             C.byref(til) if til is not None else None, _stream()), "spmm")
+
+
+def row_softmax(X, out=None):
+    out = torch.empty_like(X) if out is None else out
+    N.check(N.lib().llmrec_row_softmax_f32(_p(_mat(X)), _ld(X), _p(_mat(out)), _ld(out), X.shape[0], X.shape[1], _stream()), "row_softmax")
+    return out
+
+
+def row_softmax_bwd(S, dS, out=None):
+    out = torch.empty((S.shape[0], S.shape[1]), dtype=torch.float32, device=S.device) if out is None else out
+    N.check(N.lib().llmrec_row_softmax_bwd_f32(_p(_mat(S)), _ld(S), _p(_mat(dS)), _ld(dS), _p(_mat(out)), _ld(out),
+                                                S.shape[0], S.shape[1], _stream()), "row_softmax_bwd")
+    return out
+
+
+PROJ_MODE = {"3xtf32": 0, "tf32": 1, "fp32": 2}
+
+
+def proj_fwd(X, W, b, out, mode=0):
+    """out[n x d] = X[n x k] W[d x k]^T + b  (nn.Linear; Models.py:145-150)."""
+    _mat(X); _mat(out)
+    n, k = X.shape
+    d = W.shape[0]
+    if not W.is_contiguous() or W.shape[1] != k or out.shape != (n, d):
+        raise ValueError("proj_fwd: bad shapes")
+    N.check(N.lib().llmrec_proj_fwd_f32(_p(X), _ld(X), _p(W), _p(b), _p(out), _ld(out), n, k, d, mode, _stream()), "proj_fwd")
+    return out
+
+
+_wgrad_scratch = {}
+
+
+def proj_wgrad(X, dY, dW, db, accumulate=False, mode=0):
+    """dW[d x k] (+)= dY^T X ; db[d] (+)= colsum(dY)."""
+    _mat(X); _mat(dY)
+    n, k = X.shape
+    d = dY.shape[1]
+    need = int(N.lib().llmrec_proj_wgrad_scratch(n, k, d, mode))
+    scratch = None
+    if need:
+        key = (X.device.index, need)
+        scratch = _wgrad_scratch.get(key)
+        if scratch is None:
+            scratch = torch.empty(need, dtype=torch.float32, device=X.device)
+            _wgrad_scratch.clear()
+            _wgrad_scratch[key] = scratch
+    N.check(N.lib().llmrec_proj_wgrad_f32(_p(X), _ld(X), _p(dY), _ld(dY), _p(dW), _p(db), n, k, d, 1 if accumulate else 0, mode,
+                                           _p(scratch), need, _stream()), "proj_wgrad")
+
+
+def _ptr_table(tensors):
+    arr = (C.c_void_p * max(1, len(tensors)))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr() if t is not None else None
+    return arr
+
+
+def _ld_table(tensors):
+    arr = (C.c_int64 * max(1, len(tensors)))()
+    for i, t in enumerate(tensors):
+        arr[i] = _ld(t) if t is not None else 0
+    return arr
+
+
+def fuse_fwd(layers, sides, coefs, out, rows=None):
+    """out = mean(layers) + sum_t coefs[t] * normalize(sides[t])   (Models.py:185-197)."""
+    for t in list(layers) + list(sides) + [out]:
+        _mat(t)
+    n = out.shape[0] if rows is None else rows.numel()
+    cf = (C.c_float * max(1, len(coefs)))(*[float(c) for c in coefs])
+    N.check(N.lib().llmrec_fuse_fwd_f32(_ptr_table(layers), _ld_table(layers), len(layers), _ptr_table(sides), _ld_table(sides), cf,
+                                         len(sides), _p(out), _ld(out), _p(rows), n, out.shape[1], _stream()), "fuse_fwd")
+    return out
+
+
+def fuse_bwd(g, n_layers, d_layer, sides, coefs, d_sides, accumulate, rows=None):
+    _mat(g)
+    n = g.shape[0] if rows is None else rows.numel()
+    cf = (C.c_float * max(1, len(coefs)))(*[float(c) for c in coefs])
+    N.check(N.lib().llmrec_fuse_bwd_f32(_p(g), _ld(g), n_layers, _p(d_layer), _ld(d_layer) if d_layer is not None else 0,
+                                         _ptr_table(sides), _ld_table(sides), cf, _ptr_table(d_sides), _ld_table(d_sides), len(sides),
+                                         1 if accumulate else 0, _p(rows), n, g.shape[1], _stream()), "fuse_bwd")
+
+
+def bpr_work(n_heads, B, device):
+    return torch.zeros(int(N.lib().llmrec_bpr_work_elems(n_heads, B)), dtype=torch.float32, device=device)
+
+
+def bpr_heads(heads, users, pos, neg, n_keep, regs0_over_bs, out, loss, work):
+    """heads: list of (XU, XI, GU|None, GI|None, w_mf, w_emb).  See include/llmrec_b200.h."""
+    arr = (N.BprHead * len(heads))()
+    d = int(heads[0][0].shape[1])
+    for i, (XU, XI, GU, GI, wmf, wemb) in enumerate(heads):
+        _mat(XU); _mat(XI)
+        arr[i] = N.BprHead(_p(XU), _p(XI), _p(GU), _p(GI), _ld(XU), _ld(XI), _ld(GU) if GU is not None else 0,
+                           _ld(GI) if GI is not None else 0, float(wmf), float(wemb))
+    B = int(users.numel())
+    N.check(N.lib().llmrec_bpr_heads_f32(arr, len(heads), _p(_i32(users)), _p(_i32(pos)), _p(_i32(neg)), B, int(n_keep),
+                                          float(regs0_over_bs), d, _p(out), _p(loss), _p(work), _stream()), "bpr_heads")
+
+
+_partial = {}
+
+
+def sqnorm_grad(X, G, c, accumulate, loss):
+    """loss += c*0.5*sum(X^2); G = (G if accumulate else 0) + c*X   (feat_reg, main.py:151-156)."""
+    _mat(X)
+    part = _partial.get(X.device.index)
+    if part is None:
+        part = _partial[X.device.index] = torch.empty(1024, dtype=torch.float32, device=X.device)
+    N.check(N.lib().llmrec_sqnorm_grad_f32(_p(X), _ld(X), _p(G), _ld(G) if G is not None else 0, X.shape[0], X.shape[1], float(c),
+                                            1 if accumulate else 0, _p(loss), _p(part), _stream()), "sqnorm_grad")
+
+
+class AdamW:
+    """Dense fused AdamW over a fixed list of parameter tensors (torch.optim.AdamW defaults)."""
+
+    def __init__(self, params, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01):
+        self.params = [p for p in params]
+        self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
+        dev = self.params[0].device
+        self.m = [torch.zeros_like(p, memory_format=torch.contiguous_format) for p in self.params]
+        self.v = [torch.zeros_like(p, memory_format=torch.contiguous_format) for p in self.params]
+        self.state = torch.zeros(4, dtype=torch.float64, device=dev)
+        self._n = (C.c_int64 * len(self.params))(*[p.numel() for p in self.params])
+
+    def step(self, grads):
+        lib = N.lib()
+        N.check(lib.llmrec_adamw_advance(_p(self.state), self.lr, self.betas[0], self.betas[1], _stream()), "adamw_advance")
+        N.check(lib.llmrec_adamw_step_f32(_ptr_table([p.data for p in self.params]), _ptr_table(grads), _ptr_table(self.m), _ptr_table(self.v),
+                                           self._n, len(self.params), _p(self.state), self.lr, self.betas[0], self.betas[1], self.eps,
+                                           self.wd, _stream()), "adamw_step")
+
+
+SCORE_MODE = {"3xtf32": 0, "fp32": 2}
+_score_scratch = {}
+
+
+def score_topk(U, I, users, mask_rowptr, mask_col, K, mode=0, want_vals=False):
+    """Top-K item ids per user among items not in the user's mask row; ties -> lowest id."""
+    _mat(U); _mat(I)
+    nb, ni, d = int(users.numel()), int(I.shape[0]), int(I.shape[1])
+    idx = torch.empty((nb, K), dtype=torch.int32, device=U.device)
+    val = torch.empty((nb, K), dtype=torch.float32, device=U.device) if want_vals else None
+    need = int(N.lib().llmrec_score_topk_scratch(nb, ni, d, K, mode))
+    key = U.device.index
+    scratch = _score_scratch.get(key)
+    if need and (scratch is None or scratch.numel() < need):
+        scratch = _score_scratch[key] = torch.empty(need, dtype=torch.float32, device=U.device)
+    N.check(N.lib().llmrec_score_topk_f32(_p(U), _ld(U), _p(I), _ld(I), _p(_i32(users)), nb, ni, d, _p(mask_rowptr), _p(mask_col), K,
+                                           _p(idx), _p(val), mode, _p(scratch), scratch.numel() if scratch is not None else 0,
+                                           _stream()), "score_topk")
+    return (idx, val) if want_vals else idx
+
+
+def topk_hits(idx, users, truth_rowptr, truth_col):
+    hits = torch.empty(idx.shape, dtype=torch.uint8, device=idx.device)
+    N.check(N.lib().llmrec_topk_hits(_p(_i32(idx)), idx.shape[0], idx.shape[1], _p(_i32(users)), _p(_i32(truth_rowptr)), _p(_i32(truth_col)),
+                                      _p(hits), _stream()), "topk_hits")
+    return hits
+
+
+def fill(t, v):
+    N.check(N.lib().llmrec_fill_f32(_p(t), t.numel(), float(v), _stream()), "fill")

@@ -1,0 +1,81 @@
+"""Full-catalog evaluation with the reference's `test_torch` signature (utility/batch_test.py:112-169).
+
+The reference scores a block of users on the device, copies the whole [2048 x n_items] block to
+the host and ranks every user in Python (set difference + heapq.nlargest, ~3.7 ms/user).  Here
+scoring, train-item masking and top-max(Ks) selection (ties -> lowest item id) are ONE device op
+(`llmrec_score_topk_f32`), the hit lookup another, and only the [n x max(Ks)] 0/1 hit matrix crosses
+PCIe; metrics are the reference's float64 formulas applied to that matrix.
+"""
+import numpy as np
+import torch
+
+from .. import ops
+from ..runtime import get_args
+from . import metrics
+
+data_generator = None          # module-global like the reference (batch_test.py:16); set by init()
+Ks = [10, 20, 50]
+BATCH_SIZE = 1024
+_dev_cache = {}
+
+
+def init(generator, args=None):
+    global data_generator, Ks, BATCH_SIZE, USR_NUM, ITEM_NUM, N_TRAIN, N_TEST
+    args = args or get_args()
+    data_generator = generator
+    Ks = eval(args.Ks)
+    BATCH_SIZE = args.batch_size
+    USR_NUM, ITEM_NUM = generator.n_users, generator.n_items
+    N_TRAIN, N_TEST = generator.n_train, generator.n_test
+    _dev_cache.clear()
+
+
+def _device_csr(which, device):
+    key = (which, str(device))
+    if key not in _dev_cache:
+        rp, col = data_generator.csr(which)
+        _dev_cache[key] = (torch.from_numpy(rp).to(device), torch.from_numpy(col).to(device))
+    return _dev_cache[key]
+
+
+def rank_block(ua_embeddings, ia_embeddings, user_batch, is_val, mode=None):
+    """-> (top-K ids int32 [b x Kmax] on device, hits uint8 [b x Kmax] on device)."""
+    dev = ua_embeddings.device
+    args = get_args()
+    mode = ops.SCORE_MODE.get(getattr(args, "proj_mode", "3xtf32"), 0) if mode is None else mode
+    users = torch.as_tensor(np.asarray(user_batch, dtype=np.int32)).to(dev, non_blocking=True)
+    mrp, mcol = _device_csr("train", dev)
+    trp, tcol = _device_csr("val" if is_val else "test", dev)
+    idx = ops.score_topk(ua_embeddings, ia_embeddings, users, mrp, mcol, max(Ks), mode=mode)
+    hits = ops.topk_hits(idx, users, trp, tcol)
+    return idx, hits
+
+
+def test_torch(ua_embeddings, ia_embeddings, users_to_test, is_val, drop_flag=False, batch_test_flag=False):
+    nK = len(Ks)
+    result = {"precision": np.zeros(nK), "recall": np.zeros(nK), "ndcg": np.zeros(nK), "hit_ratio": np.zeros(nK), "auc": 0.0}
+    if get_args().test_flag != "part":
+        raise NotImplementedError("test_flag='full' (AUC over the whole ranking, batch_test.py:38-68) is out of scope (SURVEY.md 8f-4)")
+    test_users = list(users_to_test)
+    n_test_users = len(test_users)
+    u_batch_size = BATCH_SIZE * 2                                             # batch_test.py:117
+    truth = data_generator.val_set if is_val else data_generator.test_set
+    ua = ua_embeddings.detach()
+    ia = ia_embeddings.detach()
+    count = 0
+    pending = []
+    for start in range(0, n_test_users, u_batch_size):
+        user_batch = test_users[start:start + u_batch_size]
+        _, hits = rank_block(ua, ia, user_batch, is_val)
+        pending.append((user_batch, hits))
+    for user_batch, hits in pending:                                          # one D2H per block, after all launches
+        h = hits.cpu().numpy()
+        n_pos = np.fromiter((len(truth[u]) for u in user_batch), dtype=np.int64, count=len(user_batch))
+        m = metrics.block_metrics(h, n_pos, Ks)
+        for k in ("precision", "recall", "ndcg", "hit_ratio"):
+            # sequential float64 accumulation in user order == the reference's `+= re[k] / n` loop (:160-165)
+            acc = np.cumsum(np.vstack([result[k][None, :], m[k] / n_test_users]), axis=0)
+            result[k] = acc[-1]
+        count += len(user_batch)
+    assert count == n_test_users
+    return result

@@ -1,0 +1,160 @@
+"""-m gpu: the assembled hot path (MM_Model / Trainer / test_torch) against the golden vectors of the
+unmodified reference and against the CPU oracle on the same seeded inputs."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TINY_FLAGS = ["--batch_size", "128", "--epoch", "1", "--debug", "--seed", "2022"]
+
+
+def _trainer(root, extra=()):
+    from llmrec_b200 import main as M
+    from llmrec_b200.runtime import set_args
+    from llmrec_b200.utility import batch_test
+    from llmrec_b200.utility.load_data import Data
+    from llmrec_b200.utility.parser import parse_args, resolve_dataset_dir
+    args = set_args(parse_args(["--data_path", root, "--dataset", "netflix"] + TINY_FLAGS + list(extra)))
+    M.set_seed(args.seed)
+    gen = Data(path=resolve_dataset_dir(args.data_path, args.dataset), batch_size=args.batch_size, sampler=args.host_sampler)
+    batch_test.init(gen, args)
+    return M.Trainer(data_config={}, data_generator=gen), gen, M
+
+
+@pytest.mark.parametrize("mode", ["3xtf32", "fp32"])
+def test_forward_matches_reference_golden(tiny_root, golden, mode):
+    tr, gen, M = _trainer(tiny_root, ["--proj_mode", mode])
+    sd = tr.model_mm.state_dict()
+    for k in ("image_trans.weight", "user_id_embedding.weight", "item_trans.bias"):
+        np.testing.assert_array_equal(sd[k].cpu().numpy()[:8], golden["init/" + k])          # same RNG order as the reference
+    out = tr.model_mm(tr.ui_graph, tr.iu_graph, tr.image_ui_graph, tr.image_iu_graph, tr.text_ui_graph, tr.text_iu_graph)
+    assert len(out) == 14
+    U, I, img_i, txt_i, img_u, txt_u, p_usr, att_i, prof_u, prof_i, att_u, att_i2, _, _ = out
+    tol = dict(rtol=3e-5, atol=3e-6)
+    np.testing.assert_allclose(U.detach().cpu().numpy(), golden["fwd/U"], **tol)
+    np.testing.assert_allclose(I.detach().cpu().numpy(), golden["fwd/I"], **tol)
+    for name, t in (("img_i", img_i), ("txt_i", txt_i), ("img_u", img_u), ("txt_u", txt_u), ("p_usr", p_usr), ("prof_u", prof_u), ("prof_i", prof_i)):
+        np.testing.assert_allclose(t.detach().cpu().numpy()[:32], golden["fwd/" + name], **tol)
+    for k in att_i:
+        np.testing.assert_allclose(att_u[k].detach().cpu().numpy()[:32], golden["fwd/att_u/" + k], **tol)
+        np.testing.assert_allclose(att_i[k].detach().cpu().numpy()[:32], golden["fwd/att_i/" + k], **tol)
+
+
+def test_autograd_through_model_matches_reference_grads(tiny_root, golden):
+    """loss assembled with the Trainer's torch-level bpr_loss API; gradients via the custom backward."""
+    tr, gen, M = _trainer(tiny_root, ["--proj_mode", "fp32"])
+    users, pos, neg = (golden["batch/" + k].tolist() for k in ("users", "pos", "neg"))
+    out = tr.model_mm(tr.ui_graph, tr.iu_graph)
+    U, I, img_i, txt_i, img_u, txt_u, _, att_i, prof_u, prof_i, att_u, _, _, _ = out
+    a = tr.args
+    mf, emb, _ = tr.bpr_loss(U[users], I[pos], I[neg])
+    mf_i, _, _ = tr.bpr_loss(img_u[users], img_i[pos], img_i[neg])
+    mf_t, _, _ = tr.bpr_loss(txt_u[users], txt_i[pos], txt_i[neg])
+    aug = 0
+    for k in att_i:
+        t, _, _ = tr.bpr_loss(prof_u[users], att_i[k][pos], att_i[k][neg])
+        aug = aug + t
+    feat = tr.feat_reg_loss_calculation(img_i, txt_i, img_u, txt_u)
+    total = mf + emb + feat + a.aug_mf_rate * aug + a.mm_mf_rate * (mf_i + mf_t)
+    total.backward()
+    got = np.array([float(total), float(mf), float(emb), float(feat), float(aug), float(mf_i), float(mf_t)])
+    np.testing.assert_allclose(got, golden["loss/parts"], rtol=2e-5, atol=1e-9)
+    for name, p in tr.model_mm.named_parameters():
+        if name.startswith("batch_norm"):
+            continue
+        ref = golden["grad/" + name]
+        np.testing.assert_allclose(p.grad.cpu().numpy(), ref, rtol=2e-3, atol=1e-9 + 2e-5 * np.abs(ref).max(), err_msg=name)
+
+
+@pytest.mark.parametrize("mode", ["3xtf32", "fp32"])
+def test_fused_step_grads_match_reference(tiny_root, golden, mode):
+    tr, gen, M = _trainer(tiny_root, ["--proj_mode", mode])
+    users, pos, neg = (golden["batch/" + k].tolist() for k in ("users", "pos", "neg"))
+    u, p, n = tr.upload_batch(users, pos, neg)
+    hp = tr.hot
+    hp.forward()
+    hp.loss_and_output_grads(u, p, n)
+    grads = hp.backward()
+    parts = golden["loss/parts"]
+    assert abs(float(hp.loss) - parts[0]) < 2e-5 * abs(parts[0])
+    ho = hp.head_out.cpu().view(-1, 4)
+    assert abs(float(ho[0, 0]) - parts[1]) < 1e-5 and abs(float(ho[0, 1]) - parts[2]) < 1e-9
+    for name, gten in grads.items():
+        ref = golden["grad/" + name]
+        np.testing.assert_allclose(gten.cpu().numpy(), ref, rtol=2e-3, atol=1e-9 + 2e-5 * np.abs(ref).max(), err_msg=name)
+
+
+@pytest.mark.parametrize("mode", ["3xtf32", "fp32"])
+def test_epoch_matches_reference_golden(tiny_root, golden, mode):
+    """Same seed, same sampler stream, 8 steps of AdamW, then full-catalog eval: params, epoch loss, metrics, hit vectors."""
+    tr, gen, M = _trainer(tiny_root, ["--proj_mode", mode])
+    M.set_seed(2022)
+    logs = []
+    tr.logger.logging = lambda s: logs.append(str(s))
+    tr.train()
+    line = [s for s in logs if s.startswith("Epoch 0 [")][0]
+    ref_line = str(golden["epoch1/log"])
+    loss, mf = (float(x) for x in line.split("train==[")[1].split("+")[0].split("="))
+    rloss, rmf = (float(x) for x in ref_line.split("train==[")[1].split("+")[0].split("="))
+    assert abs(loss - rloss) < 5e-4 and abs(mf - rmf) < 5e-4, (line, ref_line)
+    sd = tr.model_mm.state_dict()
+    for k in sd:
+        if k.startswith("batch_norm"):
+            continue
+        np.testing.assert_allclose(sd[k].cpu().numpy(), golden["epoch1/" + k], rtol=2e-4, atol=2e-6, err_msg=k)
+    res = tr.test(list(gen.test_set.keys()), is_val=False)
+    for k in ("precision", "recall", "ndcg", "hit_ratio"):
+        np.testing.assert_allclose(res[k], golden["epoch1/metric/" + k], rtol=0, atol=1e-4)     # north_star tolerance
+    from llmrec_b200.utility import batch_test
+    ua, ia = tr.hot.forward()
+    users = sorted(gen.test_set.keys())
+    _, hits = batch_test.rank_block(ua, ia, users, False)
+    mism = int((hits.cpu().numpy() != golden["epoch1/hits"]).sum())
+    assert mism <= 2, mism
+
+
+def test_sampler_stream_matches_reference(tiny_root, golden):
+    tr, gen, M = _trainer(tiny_root)
+    M.set_seed(2022)
+    for b in range(3):
+        u, p, n = tr.sample_batch()
+        np.testing.assert_array_equal(np.asarray([u, p, n]), golden[f"sampler/{b}"])
+
+
+def test_no_feature_mode_and_layers(tiny_root):
+    """ID-only propagation (the large synthetic configuration) vs the oracle's ID chain, L = 1 and 3."""
+    from llmrec_b200.engine import HotPath, HotPathConfig
+    from llmrec_b200.graph import BipartiteGraph
+    from oracle import llmrec_oracle as O
+    data = O.load_dataset(os.path.join(tiny_root, "netflix_valid_item"))
+    for L in (1, 3):
+        torch.manual_seed(L)
+        Eu, Ei = torch.randn(data.n_users, 64) * 0.1, torch.randn(data.n_items, 64) * 0.1
+        g = BipartiteGraph(data.train_mat, "cuda")
+        params = {"user_id_embedding.weight": Eu.cuda(), "item_id_embedding.weight": Ei.cuda()}
+        hp = HotPath((g.ui, g.iu, g.uiT, g.iuT), params, None, HotPathConfig(embed_size=64, n_layers=L, batch_size=128))
+        U, I = hp.forward()
+        ui, iu = O.build_graphs(data.train_mat)
+        eu, ei = Eu.clone().requires_grad_(True), Ei.clone().requires_grad_(True)
+        us, its, a, b = [eu], [ei], eu, ei
+        for l in range(L):
+            a = torch.mm(ui, b); a = torch.softmax(a, -1) if l == L - 1 else a
+            b = torch.mm(iu, a); b = torch.softmax(b, -1) if l == L - 1 else b
+            us.append(a); its.append(b)
+        Ur, Ir = torch.mean(torch.stack(us), 0), torch.mean(torch.stack(its), 0)
+        torch.testing.assert_close(U.cpu(), Ur.detach(), rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(I.cpu(), Ir.detach(), rtol=1e-5, atol=1e-6)
+        rng = np.random.default_rng(L)
+        users = torch.from_numpy(rng.integers(0, data.n_users, 140)); pos = torch.from_numpy(rng.integers(0, data.n_items, 140)); neg = torch.from_numpy(rng.integers(0, data.n_items, 140))
+        cfg = O.OracleConfig(batch_size=128)
+        mf, emb = O.bpr_head(Ur[users], Ir[pos], Ir[neg], cfg)
+        (mf + emb).backward()
+        i32 = lambda t: t.to(torch.int32).cuda()
+        hp.loss_and_output_grads(i32(users), i32(pos), i32(neg))
+        grads = hp.backward()
+        assert abs(float(hp.loss) - float(mf + emb)) < 1e-5
+        torch.testing.assert_close(grads["user_id_embedding.weight"].cpu(), eu.grad, rtol=1e-3, atol=1e-8)
+        torch.testing.assert_close(grads["item_id_embedding.weight"].cpu(), ei.grad, rtol=1e-3, atol=1e-8)
