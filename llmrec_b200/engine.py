@@ -16,6 +16,7 @@ Every operand that shares a sparsity pattern rides in ONE SpMM launch (segments)
 """
 from __future__ import annotations
 
+import contextlib
 from dataclasses import dataclass
 
 import torch
@@ -42,6 +43,29 @@ class HotPathConfig:
 PARAM_ORDER = ("image_trans.weight", "image_trans.bias", "text_trans.weight", "text_trans.bias",
                "user_trans.weight", "user_trans.bias", "item_trans.weight", "item_trans.bias",
                "user_id_embedding.weight", "item_id_embedding.weight")
+
+
+class KernelTimer:
+    """CUDA-event timer per kernel family on the current stream (bench.py's roofline leg)."""
+
+    def __init__(self):
+        self.spans = []
+
+    @contextlib.contextmanager
+    def span(self, name):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        yield
+        b.record()
+        self.spans.append((name, a, b))
+
+    def totals(self):
+        """name -> (total ms, count) ; call after a synchronize."""
+        out = {}
+        for name, a, b in self.spans:
+            t, c = out.get(name, (0.0, 0))
+            out[name] = (t + a.elapsed_time(b), c + 1)
+        return out
 
 
 class HotPath:
@@ -82,6 +106,10 @@ class HotPath:
         self.head_out = torch.zeros(self.n_heads * 4, dtype=torch.float32, device=dev)
         self._bpr_work = None
         self.opt = None
+        self.timer = None
+
+    def _t(self, name):
+        return self.timer.span(name) if self.timer is not None else contextlib.nullcontext()
 
     # ---- column-block views ------------------------------------------------------------------
     def blk(self, buf, s):
@@ -103,11 +131,12 @@ class HotPath:
         d, L, S, m = self.d, self.L, self.S, self.cfg.proj_mode
         p, f = self.p, self.feats
         if self.has_feats:
-            ops.proj_fwd(f["image"], p["image_trans.weight"], p["image_trans.bias"], self.blk(self.Pi, 0), m)     # Models.py:145
-            ops.proj_fwd(f["text"], p["text_trans.weight"], p["text_trans.bias"], self.blk(self.Pi, 1), m)        # :146
-            for j, k in enumerate(self.keys):                                                                        # :148-150
-                ops.proj_fwd(f["item"][k], p["item_trans.weight"], p["item_trans.bias"], self.blk(self.Pi, 2 + j), m)
-            ops.proj_fwd(f["user"], p["user_trans.weight"], p["user_trans.bias"], self.P_usr, m)                  # :147
+            with self._t("proj_fwd"):
+                ops.proj_fwd(f["image"], p["image_trans.weight"], p["image_trans.bias"], self.blk(self.Pi, 0), m)     # Models.py:145
+                ops.proj_fwd(f["text"], p["text_trans.weight"], p["text_trans.bias"], self.blk(self.Pi, 1), m)        # :146
+                for j, k in enumerate(self.keys):                                                                        # :148-150
+                    ops.proj_fwd(f["item"][k], p["item_trans.weight"], p["item_trans.bias"], self.blk(self.Pi, 2 + j), m)
+                ops.proj_fwd(f["user"], p["user_trans.weight"], p["user_trans.bias"], self.P_usr, m)                  # :147
         # step t even: ui (I_{t/2} -> U_{t/2+1});  t odd: iu (U_{(t+1)/2} -> I_{(t+1)/2}); softmax on the last layer
         n_steps = max(2 * L, 3 if self.has_feats else 0)
         for t in range(n_steps):
@@ -120,7 +149,8 @@ class HotPath:
                     segs.append((self.prof_i, self.prof_u, None, False))                                               # :167
                 if l <= L:
                     segs.append((self.Il[l - 1], self.Ul[l], None, l == L))                                            # :174,178
-                self.ui.apply(segs)
+                with self._t("spmm_fwd"):
+                    self.ui.apply(segs)
             else:
                 l = (t + 1) // 2
                 if self.has_feats and t == 1:
@@ -128,7 +158,8 @@ class HotPath:
                     segs.append((self.P_usr, self.prof_i, None, False))                                                # :166
                 if l <= L:
                     segs.append((self.Ul[l], self.Il[l], None, l == L))                                                # :175,180
-                self.iu.apply(segs)
+                with self._t("spmm_fwd"):
+                    self.iu.apply(segs)
         c = self.cfg
         if self.has_feats:
             coefs = [c.model_cat_rate, c.model_cat_rate, c.user_cat_rate] + [c.item_cat_rate] * len(self.keys)
@@ -136,8 +167,9 @@ class HotPath:
             si = [self.blk(self.Fi, 0), self.blk(self.Fi, 1), self.prof_i] + [self.blk(self.Fi, 2 + j) for j in range(len(self.keys))]
         else:
             coefs, su, si = [], [], []
-        ops.fuse_fwd(self.Ul, su, coefs, self.U)                                                                       # :185-197
-        ops.fuse_fwd(self.Il, si, coefs, self.I)
+        with self._t("fuse_fwd"):
+            ops.fuse_fwd(self.Ul, su, coefs, self.U)                                                                   # :185-197
+            ops.fuse_fwd(self.Il, si, coefs, self.I)
         self._fuse_args = (coefs, su, si)
         return self.U, self.I
 
@@ -150,41 +182,48 @@ class HotPath:
             dsi = [self.blk(self.GFi, 0), self.blk(self.GFi, 1), self.Gprof_i] + [self.blk(self.GFi, 2 + j) for j in range(len(self.keys))]
         else:
             dsu, dsi = [], []
-        ops.fuse_bwd(self.gU, L + 1, self.dUl, su, coefs, dsu, True)
-        ops.fuse_bwd(self.gI, L + 1, self.dIl, si, coefs, dsi, True)
+        with self._t("fuse_bwd"):
+            ops.fuse_bwd(self.gU, L + 1, self.dUl, su, coefs, dsu, True)
+            ops.fuse_bwd(self.gI, L + 1, self.dIl, si, coefs, dsi, True)
         if self.has_feats:
             # prof_u = ui . prof_i  ->  Gprof_i += ui^T Gprof_u
-            self.uiT.apply([(self.Gprof_u, self.Gprof_i, self.Gprof_i, False)])
+            with self._t("spmm_bwd"):
+                self.uiT.apply([(self.Gprof_u, self.Gprof_i, self.Gprof_i, False)])
         gE_i = self.grads["item_id_embedding.weight"]
         g_cur_I = self.dIl
         for l in range(L, 0, -1):
             # I_l = [softmax] iu . U_l
             if l == L:
-                src = ops.row_softmax_bwd(self.Il[l], g_cur_I, out=self.tmpI)
+                with self._t("softmax_bwd"):
+                    src = ops.row_softmax_bwd(self.Il[l], g_cur_I, out=self.tmpI)
             else:
                 src = g_cur_I
             segs = [(src, self.bufU, self.dUl, False)]
             if self.has_feats and l == L:
                 segs += [(self.blk(self.GFi, s), self.blk(self.GFu, s), self.blk(self.GFu, s), False) for s in range(S)]
                 segs.append((self.Gprof_i, self.GP_usr, gp_usr_direct, False))
-            self.iuT.apply(segs)
+            with self._t("spmm_bwd"):
+                self.iuT.apply(segs)
             # U_l = [softmax] ui . I_{l-1}
             if l == L:
-                ops.row_softmax_bwd(self.Ul[l], self.bufU, out=self.bufU)
+                with self._t("softmax_bwd"):
+                    ops.row_softmax_bwd(self.Ul[l], self.bufU, out=self.bufU)
             dst = gE_i if l == 1 else self.bufI
             segs = [(self.bufU, dst, self.dIl, False)]
             if self.has_feats and l == L:
                 segs += [(self.blk(self.GFu, s), self.blk(self.GPi, s), self.blk(gpi_direct, s) if gpi_direct is not None else None, False)
                          for s in range(S)]
-            self.uiT.apply(segs)
+            with self._t("spmm_bwd"):
+                self.uiT.apply(segs)
             g_cur_I = dst
         if self.has_feats:
             f, g = self.feats, self.grads
-            ops.proj_wgrad(f["image"], self.blk(self.GPi, 0), g["image_trans.weight"], g["image_trans.bias"], False, m)
-            ops.proj_wgrad(f["text"], self.blk(self.GPi, 1), g["text_trans.weight"], g["text_trans.bias"], False, m)
-            for j, k in enumerate(self.keys):
-                ops.proj_wgrad(f["item"][k], self.blk(self.GPi, 2 + j), g["item_trans.weight"], g["item_trans.bias"], j > 0, m)
-            ops.proj_wgrad(f["user"], self.GP_usr, g["user_trans.weight"], g["user_trans.bias"], False, m)
+            with self._t("proj_wgrad"):
+                ops.proj_wgrad(f["image"], self.blk(self.GPi, 0), g["image_trans.weight"], g["image_trans.bias"], False, m)
+                ops.proj_wgrad(f["text"], self.blk(self.GPi, 1), g["text_trans.weight"], g["text_trans.bias"], False, m)
+                for j, k in enumerate(self.keys):
+                    ops.proj_wgrad(f["item"][k], self.blk(self.GPi, 2 + j), g["item_trans.weight"], g["item_trans.bias"], j > 0, m)
+                ops.proj_wgrad(f["user"], self.GP_usr, g["user_trans.weight"], g["user_trans.bias"], False, m)
         return self.grads
 
     # ---- losses + their gradients w.r.t. the forward outputs ---------------------------------------------
@@ -195,20 +234,24 @@ class HotPath:
         n_keep = int((1 - c.prune_loss_drop_rate) * B)                     # main.py:161-162 (double arithmetic)
         if self._bpr_work is None or self._bpr_work[0] != B:
             self._bpr_work = (B, ops.bpr_work(self.n_heads, B, users.device))
-        self.loss.zero_()
-        self.gU.zero_(); self.gI.zero_()
+        with self._t("memset"):
+            self.loss.zero_()
+            self.gU.zero_(); self.gI.zero_()
+            if self.has_feats:
+                self.GFu.zero_(); self.GFi.zero_(); self.Gprof_u.zero_(); self.Gprof_i.zero_()
         heads = [(self.U, self.I, self.gU, self.gI, 1.0, 1.0)]                                                        # main.py:232-235
         if self.has_feats:
-            self.GFu.zero_(); self.GFi.zero_(); self.Gprof_u.zero_(); self.Gprof_i.zero_()
             creg = c.feat_reg_decay / self.ni                                                                          # main.py:151-156
             d2 = 2 * self.d
-            ops.sqnorm_grad(self.Fu[:, :d2], self.GFu[:, :d2], creg, False, self.loss)
-            ops.sqnorm_grad(self.Fi[:, :d2], self.GFi[:, :d2], creg, False, self.loss)
+            with self._t("feat_reg"):
+                ops.sqnorm_grad(self.Fu[:, :d2], self.GFu[:, :d2], creg, False, self.loss)
+                ops.sqnorm_grad(self.Fi[:, :d2], self.GFi[:, :d2], creg, False, self.loss)
             heads.append((self.blk(self.Fu, 0), self.blk(self.Fi, 0), self.blk(self.GFu, 0), self.blk(self.GFi, 0), c.mm_mf_rate, 0.0))  # :238-241
             heads.append((self.blk(self.Fu, 1), self.blk(self.Fi, 1), self.blk(self.GFu, 1), self.blk(self.GFi, 1), c.mm_mf_rate, 0.0))  # :242-246
             for j in range(len(self.keys)):                                                                            # :248-254
                 heads.append((self.prof_u, self.blk(self.Fi, 2 + j), self.Gprof_u, self.blk(self.GFi, 2 + j), c.aug_mf_rate, 0.0))
-        ops.bpr_heads(heads, users, pos, neg, n_keep, c.regs0 / c.batch_size, self.head_out, self.loss, self._bpr_work[1])
+        with self._t("bpr"):
+            ops.bpr_heads(heads, users, pos, neg, n_keep, c.regs0 / c.batch_size, self.head_out, self.loss, self._bpr_work[1])
         return self.loss
 
     def train_step(self, users, pos, neg):
@@ -218,7 +261,8 @@ class HotPath:
         self.forward()
         self.loss_and_output_grads(users, pos, neg)
         self.backward()
-        self.opt.step([self.grads[k] for k in self._opt_names])
+        with self._t("adamw"):
+            self.opt.step([self.grads[k] for k in self._opt_names])
         return self.loss
 
     def set_optimizer(self, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01):

@@ -13,6 +13,13 @@ import torch
 from . import _native as N
 
 
+STATS = {"launches": 0}     # kernels of libllmrec_b200 launched through this module (bench.py reports it)
+
+
+def _count(n=1):
+    STATS["launches"] += n
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -104,11 +111,14 @@ class CsrOperator:
         N.check(N.lib().llmrec_spmm_csr_f32(_p(self.rowptr), _p(self.col), _p(self.vals), _p(self.rs), _p(self.cs),
                                              self.n_rows, self.n_cols, d, arr, len(segs),
                                              C.byref(til) if til is not None else None, _stream()), "spmm")
+        groups = -(-len(segs) // max(1, min(N.MAX_SEG, 1024 // d))) if d % 4 == 0 else -(-len(segs) // N.MAX_SEG)
+        _count(groups * (2 if (til is not None and til.n_split > 0) else 1))
 
 
 def row_softmax(X, out=None):
     out = torch.empty_like(X) if out is None else out
     N.check(N.lib().llmrec_row_softmax_f32(_p(_mat(X)), _ld(X), _p(_mat(out)), _ld(out), X.shape[0], X.shape[1], _stream()), "row_softmax")
+    _count()
     return out
 
 
@@ -116,6 +126,7 @@ def row_softmax_bwd(S, dS, out=None):
     out = torch.empty((S.shape[0], S.shape[1]), dtype=torch.float32, device=S.device) if out is None else out
     N.check(N.lib().llmrec_row_softmax_bwd_f32(_p(_mat(S)), _ld(S), _p(_mat(dS)), _ld(dS), _p(_mat(out)), _ld(out),
                                                 S.shape[0], S.shape[1], _stream()), "row_softmax_bwd")
+    _count()
     return out
 
 
@@ -130,6 +141,7 @@ def proj_fwd(X, W, b, out, mode=0):
     if not W.is_contiguous() or W.shape[1] != k or out.shape != (n, d):
         raise ValueError("proj_fwd: bad shapes")
     N.check(N.lib().llmrec_proj_fwd_f32(_p(X), _ld(X), _p(W), _p(b), _p(out), _ld(out), n, k, d, mode, _stream()), "proj_fwd")
+    _count()
     return out
 
 
@@ -152,6 +164,7 @@ def proj_wgrad(X, dY, dW, db, accumulate=False, mode=0):
             _wgrad_scratch[key] = scratch
     N.check(N.lib().llmrec_proj_wgrad_f32(_p(X), _ld(X), _p(dY), _ld(dY), _p(dW), _p(db), n, k, d, 1 if accumulate else 0, mode,
                                            _p(scratch), need, _stream()), "proj_wgrad")
+    _count()
 
 
 def _ptr_table(tensors):
@@ -176,6 +189,7 @@ def fuse_fwd(layers, sides, coefs, out, rows=None):
     cf = (C.c_float * max(1, len(coefs)))(*[float(c) for c in coefs])
     N.check(N.lib().llmrec_fuse_fwd_f32(_ptr_table(layers), _ld_table(layers), len(layers), _ptr_table(sides), _ld_table(sides), cf,
                                          len(sides), _p(out), _ld(out), _p(rows), n, out.shape[1], _stream()), "fuse_fwd")
+    _count()
     return out
 
 
@@ -186,6 +200,7 @@ def fuse_bwd(g, n_layers, d_layer, sides, coefs, d_sides, accumulate, rows=None)
     N.check(N.lib().llmrec_fuse_bwd_f32(_p(g), _ld(g), n_layers, _p(d_layer), _ld(d_layer) if d_layer is not None else 0,
                                          _ptr_table(sides), _ld_table(sides), cf, _ptr_table(d_sides), _ld_table(d_sides), len(sides),
                                          1 if accumulate else 0, _p(rows), n, g.shape[1], _stream()), "fuse_bwd")
+    _count()
 
 
 def bpr_work(n_heads, B, device):
@@ -203,6 +218,7 @@ def bpr_heads(heads, users, pos, neg, n_keep, regs0_over_bs, out, loss, work):
     B = int(users.numel())
     N.check(N.lib().llmrec_bpr_heads_f32(arr, len(heads), _p(_i32(users)), _p(_i32(pos)), _p(_i32(neg)), B, int(n_keep),
                                           float(regs0_over_bs), d, _p(out), _p(loss), _p(work), _stream()), "bpr_heads")
+    _count(3)
 
 
 _partial = {}
@@ -216,6 +232,7 @@ def sqnorm_grad(X, G, c, accumulate, loss):
         part = _partial[X.device.index] = torch.empty(1024, dtype=torch.float32, device=X.device)
     N.check(N.lib().llmrec_sqnorm_grad_f32(_p(X), _ld(X), _p(G), _ld(G) if G is not None else 0, X.shape[0], X.shape[1], float(c),
                                             1 if accumulate else 0, _p(loss), _p(part), _stream()), "sqnorm_grad")
+    _count(2)
 
 
 class AdamW:
@@ -236,6 +253,7 @@ class AdamW:
         N.check(lib.llmrec_adamw_step_f32(_ptr_table([p.data for p in self.params]), _ptr_table(grads), _ptr_table(self.m), _ptr_table(self.v),
                                            self._n, len(self.params), _p(self.state), self.lr, self.betas[0], self.betas[1], self.eps,
                                            self.wd, _stream()), "adamw_step")
+        _count(1 + -(-len(self.params) // 16))
 
 
 SCORE_MODE = {"3xtf32": 0, "fp32": 2}
@@ -256,6 +274,7 @@ def score_topk(U, I, users, mask_rowptr, mask_col, K, mode=0, want_vals=False):
     N.check(N.lib().llmrec_score_topk_f32(_p(U), _ld(U), _p(I), _ld(I), _p(_i32(users)), nb, ni, d, _p(mask_rowptr), _p(mask_col), K,
                                            _p(idx), _p(val), mode, _p(scratch), scratch.numel() if scratch is not None else 0,
                                            _stream()), "score_topk")
+    _count(3)
     return (idx, val) if want_vals else idx
 
 
@@ -263,6 +282,7 @@ def topk_hits(idx, users, truth_rowptr, truth_col):
     hits = torch.empty(idx.shape, dtype=torch.uint8, device=idx.device)
     N.check(N.lib().llmrec_topk_hits(_p(_i32(idx)), idx.shape[0], idx.shape[1], _p(_i32(users)), _p(_i32(truth_rowptr)), _p(_i32(truth_col)),
                                       _p(hits), _stream()), "topk_hits")
+    _count()
     return hits
 
 

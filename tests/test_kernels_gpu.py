@@ -90,7 +90,7 @@ def test_spmm_row_tiling_long_rows(d, nseg):
         ref = dense @ X[s].cpu().double()
         if s == 0:
             ref = torch.softmax(ref, -1)
-        torch.testing.assert_close(Y[s].cpu().double(), ref, rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(Y[s].cpu().double(), ref, rtol=1e-4, atol=1e-4)   # sums of thousands of terms
     # deterministic: bitwise equal across runs
     Y2 = [torch.empty(150, d, device=cuda) for _ in range(nseg)]
     op.apply([(x, y, None, s == 0) for s, (x, y) in enumerate(zip(X, Y2))])
