@@ -88,12 +88,31 @@ int llmrec_row_softmax_bwd_f32(const float* S, int64_t lds, const float* dS, int
  * --------------------------------------------------------------------------------------------- */
 int llmrec_proj_fwd_f32(const float* X, int64_t ldx, const float* W, const float* bias,
                         float* Y, int64_t ldy, int64_t n, int32_t k, int32_t d, int32_t mode,
-                        llmrec_stream_t stream);
+                        float* wsplit /* 2*d*k floats, mode 0 only */, llmrec_stream_t stream);
 int llmrec_proj_wgrad_f32(const float* X, int64_t ldx, const float* dY, int64_t lddy,
                           float* dW, float* db, int64_t n, int32_t k, int32_t d, int32_t accumulate,
                           int32_t mode, float* scratch, int64_t scratch_elems, llmrec_stream_t stream);
 /* scratch elements needed by llmrec_proj_wgrad_f32 for this shape/mode */
 int64_t llmrec_proj_wgrad_scratch(int64_t n, int32_t k, int32_t d, int32_t mode);
+
+/* Grouped forms: all projections of one step (image, text, user, 5 attribute tables) in ONE persistent
+ * launch.  Problems that share W (the 5 attribute tables use item_trans) share `wsplit`; wgrad problems
+ * that share dW/db list them in order with accumulate = 1 after the first. */
+typedef struct {
+  const float* X; const float* W; const float* bias; float* Y; float* wsplit;
+  int64_t ldx, ldy, n;
+  int32_t k, _pad;
+} llmrec_proj_fwd_problem;
+typedef struct {
+  const float* X; const float* dY; float* dW; float* db;
+  int64_t ldx, lddy, n;
+  int32_t k, accumulate;
+} llmrec_proj_wgrad_problem;
+int llmrec_proj_fwd_group_f32(const llmrec_proj_fwd_problem* probs_host, int32_t n_prob, int32_t d, int32_t mode,
+                              llmrec_stream_t stream);
+int llmrec_proj_wgrad_group_f32(const llmrec_proj_wgrad_problem* probs_host, int32_t n_prob, int32_t d, int32_t mode,
+                                float* scratch, int64_t scratch_elems, llmrec_stream_t stream);
+int64_t llmrec_proj_wgrad_group_scratch(const llmrec_proj_wgrad_problem* probs_host, int32_t n_prob, int32_t d, int32_t mode);
 
 /* ---------------------------------------------------------------------------------------------
  * Fusion (Models.py:185-197):  out = mean(layer_0..layer_{L}) + sum_t coef[t] * x_t / max(||x_t||_2, 1e-12)

@@ -29,6 +29,16 @@ class SpmmTiling(C.Structure):
                 ("n_split_tiles", C.c_int32)]
 
 
+class ProjFwdProblem(C.Structure):
+    _fields_ = [("X", C.c_void_p), ("W", C.c_void_p), ("bias", C.c_void_p), ("Y", C.c_void_p), ("wsplit", C.c_void_p),
+                ("ldx", C.c_int64), ("ldy", C.c_int64), ("n", C.c_int64), ("k", C.c_int32), ("_pad", C.c_int32)]
+
+
+class ProjWgradProblem(C.Structure):
+    _fields_ = [("X", C.c_void_p), ("dY", C.c_void_p), ("dW", C.c_void_p), ("db", C.c_void_p),
+                ("ldx", C.c_int64), ("lddy", C.c_int64), ("n", C.c_int64), ("k", C.c_int32), ("accumulate", C.c_int32)]
+
+
 class BprHead(C.Structure):
     _fields_ = [("XU", C.c_void_p), ("XI", C.c_void_p), ("GU", C.c_void_p), ("GI", C.c_void_p),
                 ("ldxu", C.c_int64), ("ldxi", C.c_int64), ("ldgu", C.c_int64), ("ldgi", C.c_int64),
@@ -44,7 +54,10 @@ SIGNATURES = {
                                       C.POINTER(SpmmSeg), C.c_int32, C.POINTER(SpmmTiling), c_stream]),
     "llmrec_row_softmax_f32": (C.c_int, [c_f32p, C.c_int64, c_f32p, C.c_int64, C.c_int64, C.c_int32, c_stream]),
     "llmrec_row_softmax_bwd_f32": (C.c_int, [c_f32p, C.c_int64, c_f32p, C.c_int64, c_f32p, C.c_int64, C.c_int64, C.c_int32, c_stream]),
-    "llmrec_proj_fwd_f32": (C.c_int, [c_f32p, C.c_int64, c_f32p, c_f32p, c_f32p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, c_stream]),
+    "llmrec_proj_fwd_f32": (C.c_int, [c_f32p, C.c_int64, c_f32p, c_f32p, c_f32p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, c_f32p, c_stream]),
+    "llmrec_proj_fwd_group_f32": (C.c_int, [C.POINTER(ProjFwdProblem), C.c_int32, C.c_int32, C.c_int32, c_stream]),
+    "llmrec_proj_wgrad_group_f32": (C.c_int, [C.POINTER(ProjWgradProblem), C.c_int32, C.c_int32, C.c_int32, c_f32p, C.c_int64, c_stream]),
+    "llmrec_proj_wgrad_group_scratch": (C.c_int64, [C.POINTER(ProjWgradProblem), C.c_int32, C.c_int32, C.c_int32]),
     "llmrec_proj_wgrad_f32": (C.c_int, [c_f32p, C.c_int64, c_f32p, C.c_int64, c_f32p, c_f32p, C.c_int64, C.c_int32, C.c_int32,
                                         C.c_int32, C.c_int32, c_f32p, C.c_int64, c_stream]),
     "llmrec_proj_wgrad_scratch": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32, C.c_int32]),

@@ -1,0 +1,573 @@
+// Side-feature projection on the 5th-gen tensor cores (tcgen05, TMEM accumulators, TMA-fed).
+//
+//   forward  Y[n x d]  = X[n x k] W[d x k]^T + b          (nn.Linear, Models.py:145-150)
+//   wgrad    dW[d x k] = dY[n x d]^T X[n x k], db = colsum(dY)   (its autograd; X is a constant feature table)
+//
+// Both are HBM-bound (32-64 flop/B at d = 64-128): the job of the kernel is to stream X once at HBM
+// speed.  All 8 projections of a step run as ONE persistent grouped launch (148 CTAs, static tile
+// round-robin over a problem table) -- a single projection has only ~136 row tiles.
+//
+// Precision: fp32 operands are split  x = hi + lo  (hi = top 19 bits, exactly TF32-representable) by a
+// transform warp-group while the tile sits in shared memory, and three kind::tf32 MMAs accumulate
+// hi*hi + hi*lo + lo*hi in the fp32 TMEM accumulator ("3xTF32", error ~2^-21 relative per product, i.e.
+// fp32-class).  mode 1 skips the split (plain TF32, ~2^-11).
+//
+// Warp roles (384 threads, 1 CTA/SM):  w0 TMA producer | w1 MMA issuer | w2 TMEM allocator | w4-7 split
+// transform | w8-11 epilogue (TMEM -> registers -> global).  Pipelines: smem ring full/xform/empty
+// mbarriers, double-buffered TMEM accumulator with tmem_full/tmem_empty mbarriers.
+//
+// Layouts: forward operands are K-major 128-byte-swizzled tiles ([rows][32 fp32]); the wgrad contraction
+// runs over ROWS, so its operands are MN-major swizzled tiles ([32-column atom][32 rows][32 fp32]) fetched
+// as 32x32 TMA boxes -- no transpose pass over X or dY is ever materialised.
+#include <mutex>
+#include <vector>
+#include <string.h>
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace llmrec {
+
+using namespace tc;
+
+constexpr int kMaxProb = 8;
+constexpr int BM = 128;  // tile rows (fwd) / tile features (wgrad) = UMMA M
+constexpr int BK = 32;   // fp32 per 128-byte swizzle row
+constexpr uint32_t kTileA = BM * BK * 4;  // 16 KiB
+
+// ------------------------------------------------------------------------------------------------
+// host: tensor maps
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeFn get_encode() {
+  static EncodeFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeFn>(p);
+  }
+  return fn;
+}
+
+bool make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                      uint32_t box_inner, uint32_t box_outer) {
+  struct Entry { TmapKey k; CUtensorMap m; };
+  static std::vector<Entry> cache;
+  static std::mutex mu;
+  TmapKey key{base, inner, outer, row_stride_bytes, box_inner, box_outer};
+  std::lock_guard<std::mutex> lock(mu);
+  for (auto& e : cache)
+    if (memcmp(&e.k, &key, sizeof(key)) == 0) { *out = e.m; return true; }
+  EncodeFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return false; }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) inner=%llu outer=%llu stride=%llu box=%ux%u", (int)r,
+                                     (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)row_stride_bytes, box_inner, box_outer); return false; }
+  if (cache.size() > 256) cache.clear();
+  cache.push_back({key, *out});
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+struct FwdProblem { int n, k, kblocks, tile_start; long long ldy; float* Y; const float* bias; };
+struct FwdParams {
+  CUtensorMap tmA[kMaxProb];
+  CUtensorMap tmW[kMaxProb];  // [2d x k] (hi rows then lo rows) when SPLIT, [d x k] otherwise
+  FwdProblem prob[kMaxProb];
+  int n_prob, total_tiles, d, stages, tmem_cols;
+};
+
+struct PipeState {
+  int stage = 0; uint32_t phase = 0; int nstages;
+  __device__ explicit PipeState(int n) : nstages(n) {}
+  __device__ void advance() { if (++stage == nstages) { stage = 0; phase ^= 1; } }
+};
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(384, 1) proj_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int d = P.d, stages = P.stages;
+  const uint32_t b_bytes = (uint32_t)d * 128u;
+  const uint32_t stage_bytes = (kTileA + b_bytes) * (SPLIT ? 2u : 1u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
+  uint64_t* full = bars; uint64_t* xform = bars + stages; uint64_t* empty = bars + 2 * stages;
+  uint64_t* tfull = bars + 3 * stages; uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  auto sA = [&](int s) { return smem + (size_t)s * stage_bytes; };
+  auto sAlo = [&](int s) { return sA(s) + kTileA; };
+  auto sB = [&](int s) { return sA(s) + kTileA * (SPLIT ? 2u : 1u); };
+  auto sBlo = [&](int s) { return sB(s) + b_bytes; };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    for (int p = 0; p < P.n_prob; ++p) { prefetch_tmap(&P.tmA[p]); prefetch_tmap(&P.tmW[p]); }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&xform[s], 128); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto locate = [&](int tile, int& p, int& mblk) {
+    p = 0;
+    while (p + 1 < P.n_prob && tile >= P.prob[p + 1].tile_start) ++p;
+    mblk = tile - P.prob[p].tile_start;
+  };
+
+  if (warp == 0 && lane == 0) {
+    // ===== TMA producer =====
+    PipeState st(stages);
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      int p, mblk; locate(tile, p, mblk);
+      const int kb_n = P.prob[p].kblocks;
+      for (int kb = 0; kb < kb_n; ++kb) {
+        mbar_wait(&empty[st.stage], st.phase ^ 1);
+        mbar_arrive_expect_tx(&full[st.stage], kTileA + b_bytes * (SPLIT ? 2u : 1u));
+        tma_load_2d(sA(st.stage), &P.tmA[p], &full[st.stage], kb * BK, mblk * BM);
+        tma_load_2d(sB(st.stage), &P.tmW[p], &full[st.stage], kb * BK, 0);
+        if (SPLIT) tma_load_2d(sBlo(st.stage), &P.tmW[p], &full[st.stage], kb * BK, d);
+        st.advance();
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===== MMA issuer =====
+    PipeState st(stages);
+    const uint32_t idesc = idesc_tf32(BM, d, 0, 0);
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      int p, mblk; locate(tile, p, mblk);
+      const int kb_n = P.prob[p].kblocks;
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * d);
+      for (int kb = 0; kb < kb_n; ++kb) {
+        mbar_wait(SPLIT ? &xform[st.stage] : &full[st.stage], st.phase);
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(sA(st.stage)), al0 = smem_u32(sAlo(st.stage));
+        const uint32_t b0 = smem_u32(sB(st.stage)), bl0 = smem_u32(sBlo(st.stage));
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {  // UMMA_K = 8 fp32 = 32 bytes inside the 128-byte swizzle row
+          const uint64_t ad = smem_desc_sw128(a0 + kk * 32, 0, 1024);
+          const uint64_t bd = smem_desc_sw128(b0 + kk * 32, 0, 1024);
+          const uint32_t first = (kb | kk) != 0;
+          if (SPLIT) {
+            const uint64_t ald = smem_desc_sw128(al0 + kk * 32, 0, 1024);
+            const uint64_t bld = smem_desc_sw128(bl0 + kk * 32, 0, 1024);
+            umma_tf32(d_tmem, ald, bd, idesc, first);   // lo * hi
+            umma_tf32(d_tmem, ad, bld, idesc, 1);       // hi * lo
+            umma_tf32(d_tmem, ad, bd, idesc, 1);        // hi * hi
+          } else {
+            umma_tf32(d_tmem, ad, bd, idesc, first);
+          }
+        }
+        umma_commit(&empty[st.stage]);
+        st.advance();
+      }
+      umma_commit(&tfull[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (SPLIT && warp >= 4 && warp < 8) {
+    // ===== split transform: A -> A_hi (in place) + A_lo =====
+    PipeState st(stages);
+    const int tid = threadIdx.x - 128;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      int p, mblk; locate(tile, p, mblk);
+      const int kb_n = P.prob[p].kblocks;
+      for (int kb = 0; kb < kb_n; ++kb) {
+        mbar_wait(&full[st.stage], st.phase);
+        split_tile_inplace(reinterpret_cast<float4*>(sA(st.stage)), reinterpret_cast<float4*>(sAlo(st.stage)), kTileA / 16, tid, 128);
+        fence_proxy_async_smem();
+        mbar_arrive(&xform[st.stage]);
+        st.advance();
+      }
+    }
+  } else if (warp >= 8) {
+    // ===== epilogue: TMEM -> registers -> (+bias) -> global =====
+    const int wq = warp & 3;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      int p, mblk; locate(tile, p, mblk);
+      const FwdProblem pr = P.prob[p];
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const int row = mblk * BM + wq * 32 + lane;
+      const uint32_t t0 = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * d);
+      float* yrow = pr.Y + (long long)row * pr.ldy;
+      int c0 = 0;
+      for (; c0 + 32 <= d; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(t0 + c0, r);
+        tmem_ld_wait();
+        if (row < pr.n) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 b = pr.bias ? __ldg(reinterpret_cast<const float4*>(pr.bias + c0 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            st4(yrow + c0 + j, make_float4(__uint_as_float(r[j]) + b.x, __uint_as_float(r[j + 1]) + b.y,
+                                           __uint_as_float(r[j + 2]) + b.z, __uint_as_float(r[j + 3]) + b.w));
+          }
+        }
+      }
+      if (c0 < d) {  // d % 32 == 16
+        uint32_t r[16];
+        tmem_ld_32x16(t0 + c0, r);
+        tmem_ld_wait();
+        if (row < pr.n) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            float4 b = pr.bias ? __ldg(reinterpret_cast<const float4*>(pr.bias + c0 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            st4(yrow + c0 + j, make_float4(__uint_as_float(r[j]) + b.x, __uint_as_float(r[j + 1]) + b.y,
+                                           __uint_as_float(r[j + 2]) + b.z, __uint_as_float(r[j + 3]) + b.w));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols); }
+}
+
+// W -> [hi ; lo]  ([2d x k], hi exactly TF32-representable)
+__global__ void wsplit_kernel(const float* __restrict__ W, float* __restrict__ out, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) { float v = W[i]; float h = tf32_hi(v); out[i] = h; out[n + i] = v - h; }
+}
+
+static uint32_t pow2_cols(int c) { uint32_t r = 32; while ((int)r < c) r <<= 1; return r; }
+
+// ------------------------------------------------------------------------------------------------
+// wgrad
+// ------------------------------------------------------------------------------------------------
+struct WgProblem { int n, k, ft_tiles, chunks, rows_per_chunk, item_start; };
+struct WgParams {
+  CUtensorMap tmX[kMaxProb];
+  CUtensorMap tmG[kMaxProb];
+  WgProblem prob[kMaxProb];
+  int n_prob, total_items, d, stages, tmem_cols;
+  float* partial;  // [total_items][128][d]
+};
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(384, 1) proj_wgrad_tc_kernel(const __grid_constant__ WgParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int d = P.d, stages = P.stages;
+  const uint32_t b_bytes = (uint32_t)d * 128u;  // [d/32 atoms][32 rows][128 B]
+  const uint32_t stage_bytes = (kTileA + b_bytes) * (SPLIT ? 2u : 1u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
+  uint64_t* full = bars; uint64_t* xform = bars + stages; uint64_t* empty = bars + 2 * stages;
+  uint64_t* tfull = bars + 3 * stages; uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  auto sA = [&](int s) { return smem + (size_t)s * stage_bytes; };
+  auto sAlo = [&](int s) { return sA(s) + kTileA; };
+  auto sB = [&](int s) { return sA(s) + kTileA * (SPLIT ? 2u : 1u); };
+  auto sBlo = [&](int s) { return sB(s) + b_bytes; };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    for (int p = 0; p < P.n_prob; ++p) { prefetch_tmap(&P.tmX[p]); prefetch_tmap(&P.tmG[p]); }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&xform[s], 128); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // item -> (problem, feature tile, row range)
+  auto locate = [&](int item, int& p, int& ft, int& r0, int& kb_n) {
+    p = 0;
+    while (p + 1 < P.n_prob && item >= P.prob[p + 1].item_start) ++p;
+    const WgProblem pr = P.prob[p];
+    const int local = item - pr.item_start;
+    const int chunk = local / pr.ft_tiles;
+    ft = local - chunk * pr.ft_tiles;
+    r0 = chunk * pr.rows_per_chunk;
+    const int r1 = min(pr.n, r0 + pr.rows_per_chunk);
+    kb_n = (r1 - r0 + BK - 1) / BK;
+  };
+
+  if (warp == 0 && lane == 0) {
+    PipeState st(stages);
+    for (int item = blockIdx.x; item < P.total_items; item += gridDim.x) {
+      int p, ft, r0, kb_n; locate(item, p, ft, r0, kb_n);
+      for (int kb = 0; kb < kb_n; ++kb) {
+        mbar_wait(&empty[st.stage], st.phase ^ 1);
+        mbar_arrive_expect_tx(&full[st.stage], kTileA + b_bytes);
+        const int r = r0 + kb * BK;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) tma_load_2d(sA(st.stage) + a * 4096, &P.tmX[p], &full[st.stage], ft * BM + a * 32, r);
+        for (int b = 0; b < d / 32; ++b) tma_load_2d(sB(st.stage) + b * 4096, &P.tmG[p], &full[st.stage], b * 32, r);
+        st.advance();
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    PipeState st(stages);
+    const uint32_t idesc = idesc_tf32(BM, d, 1, 1);
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < P.total_items; item += gridDim.x) {
+      int p, ft, r0, kb_n; locate(item, p, ft, r0, kb_n);
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * d);
+      for (int kb = 0; kb < kb_n; ++kb) {
+        mbar_wait(SPLIT ? &xform[st.stage] : &full[st.stage], st.phase);
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(sA(st.stage)), al0 = smem_u32(sAlo(st.stage));
+        const uint32_t b0 = smem_u32(sB(st.stage)), bl0 = smem_u32(sBlo(st.stage));
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {  // UMMA_K = 8 rows = one 8 x 128 B atom along K
+          const uint64_t ad = smem_desc_sw128(a0 + kk * 1024, 4096, 1024);
+          const uint64_t bd = smem_desc_sw128(b0 + kk * 1024, 4096, 1024);
+          const uint32_t first = (kb | kk) != 0;
+          if (SPLIT) {
+            const uint64_t ald = smem_desc_sw128(al0 + kk * 1024, 4096, 1024);
+            const uint64_t bld = smem_desc_sw128(bl0 + kk * 1024, 4096, 1024);
+            umma_tf32(d_tmem, ald, bd, idesc, first);
+            umma_tf32(d_tmem, ad, bld, idesc, 1);
+            umma_tf32(d_tmem, ad, bd, idesc, 1);
+          } else {
+            umma_tf32(d_tmem, ad, bd, idesc, first);
+          }
+        }
+        umma_commit(&empty[st.stage]);
+        st.advance();
+      }
+      umma_commit(&tfull[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (SPLIT && warp >= 4 && warp < 8) {
+    PipeState st(stages);
+    const int tid = threadIdx.x - 128;
+    for (int item = blockIdx.x; item < P.total_items; item += gridDim.x) {
+      int p, ft, r0, kb_n; locate(item, p, ft, r0, kb_n);
+      for (int kb = 0; kb < kb_n; ++kb) {
+        mbar_wait(&full[st.stage], st.phase);
+        split_tile_inplace(reinterpret_cast<float4*>(sA(st.stage)), reinterpret_cast<float4*>(sAlo(st.stage)), kTileA / 16, tid, 128);
+        split_tile_inplace(reinterpret_cast<float4*>(sB(st.stage)), reinterpret_cast<float4*>(sBlo(st.stage)), (int)(b_bytes / 16), tid, 128);
+        fence_proxy_async_smem();
+        mbar_arrive(&xform[st.stage]);
+        st.advance();
+      }
+    }
+  } else if (warp >= 8) {
+    const int wq = warp & 3;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < P.total_items; item += gridDim.x) {
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t0 = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * d);
+      float* out = P.partial + ((long long)item * BM + wq * 32 + lane) * d;
+      for (int c0 = 0; c0 < d; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(t0 + c0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          st4(out + c0 + j, make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols); }
+}
+
+// dW[dc][f] (+)= sum over row chunks of partial[item][f % 128][dc]   (fixed order -> deterministic)
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int item_start, int ft_tiles, int chunks,
+                                                           int k, int d, float* __restrict__ dW, int accumulate) {
+  const int ft = blockIdx.x;
+  for (int i = threadIdx.x; i < BM * d; i += blockDim.x) {
+    const int f = i / d, dc = i - f * d;
+    const int gf = ft * BM + f;
+    if (gf >= k) continue;
+    float s = 0.f;
+    for (int c = 0; c < chunks; ++c) s += partial[((long long)(item_start + c * ft_tiles + ft) * BM + f) * d + dc];
+    float* o = dW + (long long)dc * k + gf;
+    *o = accumulate ? (*o + s) : s;
+  }
+}
+// db[dc] (+)= sum_r dY[r][dc] : 16 row-slices per problem -> partial, then an ordered combine (deterministic;
+// problems sharing one db -- the 5 attribute matrices behind item_trans -- accumulate in problem order)
+struct ColsumParams { const float* dY[kMaxProb]; long long ld[kMaxProb]; long long n[kMaxProb]; float* db[kMaxProb]; int acc[kMaxProb]; int d; int n_prob; float* partial; };
+constexpr int kColsumSlices = 16;
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const ColsumParams P) {
+  __shared__ float red[256];
+  const int p = blockIdx.y, b = blockIdx.x, d = P.d;
+  const int groups = 256 / d > 0 ? 256 / d : 1;  // d <= 256
+  const int g = threadIdx.x / d, c = threadIdx.x - g * d;
+  float s = 0.f;
+  if (g < groups && P.db[p])
+    for (long long r = (long long)b * groups + g; r < P.n[p]; r += (long long)kColsumSlices * groups) s += P.dY[p][r * P.ld[p] + c];
+  red[threadIdx.x] = (g < groups) ? s : 0.f;
+  __syncthreads();
+  if (threadIdx.x < d) {
+    float t = 0.f;
+    for (int gg = 0; gg < groups; ++gg) t += red[gg * d + threadIdx.x];
+    P.partial[((long long)p * kColsumSlices + b) * d + threadIdx.x] = t;
+  }
+}
+__global__ void __launch_bounds__(256) colsum_final_kernel(const ColsumParams P) {
+  const int c = threadIdx.x;
+  if (c >= P.d) return;
+  for (int p = 0; p < P.n_prob; ++p) {
+    if (!P.db[p]) continue;
+    float t = 0.f;
+    for (int b = 0; b < kColsumSlices; ++b) t += P.partial[((long long)p * kColsumSlices + b) * P.d + c];
+    float* o = P.db[p] + c;
+    *o = P.acc[p] ? (*o + t) : t;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host API (grouped)
+// ------------------------------------------------------------------------------------------------
+static int stages_for(int d, bool split, uint32_t* smem_bytes) {
+  const uint32_t stage = (kTileA + (uint32_t)d * 128u) * (split ? 2u : 1u);
+  int s = (int)((200u * 1024u) / stage);
+  if (s > 8) s = 8;
+  if (s < 2) s = 2;
+  *smem_bytes = (uint32_t)s * stage + 1024 /*align slack*/ + 256 /*barriers*/;
+  return s;
+}
+
+bool proj_tc_supported(int d, int64_t ldx, const void* X, int k, bool wgrad) {
+  return d % (wgrad ? 32 : 16) == 0 && d >= 16 && d <= 256 && ldx % 4 == 0 && aligned16(X) && k >= 1 && k % 4 == 0;
+}
+
+int proj_fwd_tc_group(const llmrec_proj_fwd_problem* pr, int n_prob, int d, int mode, cudaStream_t st) {
+  const bool split = (mode == 0);
+  FwdParams P;
+  memset(&P, 0, sizeof(P));
+  P.n_prob = n_prob; P.d = d;
+  int tiles = 0;
+  for (int p = 0; p < n_prob; ++p) {
+    const float* wsrc = split ? pr[p].wsplit : pr[p].W;
+    LLMREC_CHECK_ARG(!split || pr[p].wsplit, "proj_fwd: 3xTF32 mode needs a wsplit buffer of 2*d*k floats");
+    bool fresh = true;
+    for (int q = 0; q < p; ++q) fresh = fresh && !(pr[q].W == pr[p].W && pr[q].wsplit == pr[p].wsplit);
+    if (split && fresh) {
+      int64_t n = (int64_t)d * pr[p].k;
+      wsplit_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pr[p].W, pr[p].wsplit, n);
+      LLMREC_CHECK_LAUNCH("wsplit");
+    }
+    if (!make_tmap_2d_f32(&P.tmA[p], pr[p].X, (uint64_t)pr[p].k, (uint64_t)pr[p].n, (uint64_t)pr[p].ldx * 4, BK, BM)) return 4;
+    if (!make_tmap_2d_f32(&P.tmW[p], wsrc, (uint64_t)pr[p].k, (uint64_t)(split ? 2 * d : d), (uint64_t)pr[p].k * 4, BK, (uint32_t)d)) return 4;
+    P.prob[p].n = (int)pr[p].n; P.prob[p].k = pr[p].k; P.prob[p].kblocks = (pr[p].k + BK - 1) / BK;
+    P.prob[p].tile_start = tiles; P.prob[p].ldy = pr[p].ldy; P.prob[p].Y = pr[p].Y; P.prob[p].bias = pr[p].bias;
+    tiles += (int)((pr[p].n + BM - 1) / BM);
+  }
+  P.total_tiles = tiles;
+  uint32_t smem;
+  P.stages = stages_for(d, split, &smem);
+  P.tmem_cols = (int)pow2_cols(2 * d);
+  int grid = tiles < 148 ? tiles : 148;
+  if (grid <= 0) return 0;
+  if (split) {
+    cudaFuncSetAttribute(proj_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    proj_fwd_tc_kernel<true><<<grid, 384, smem, st>>>(P);
+  } else {
+    cudaFuncSetAttribute(proj_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    proj_fwd_tc_kernel<false><<<grid, 384, smem, st>>>(P);
+  }
+  LLMREC_CHECK_LAUNCH("proj_fwd_tc");
+  return 0;
+}
+
+static int wg_rows_per_chunk(int64_t n) {
+  int r = 2048;
+  while (r > 256 && n / r < 4) r >>= 1;
+  return r;
+}
+
+int64_t proj_wgrad_tc_scratch(const llmrec_proj_wgrad_problem* pr, int n_prob, int d) {
+  int64_t items = 0;
+  for (int p = 0; p < n_prob; ++p) {
+    int rpc = wg_rows_per_chunk(pr[p].n);
+    items += (int64_t)((pr[p].k + BM - 1) / BM) * ((pr[p].n + rpc - 1) / rpc);
+  }
+  return items * BM * d + (int64_t)n_prob * kColsumSlices * d;
+}
+
+int proj_wgrad_tc_group(const llmrec_proj_wgrad_problem* pr, int n_prob, int d, int mode, float* scratch, int64_t scratch_elems, cudaStream_t st) {
+  const bool split = (mode == 0);
+  WgParams P;
+  memset(&P, 0, sizeof(P));
+  P.n_prob = n_prob; P.d = d;
+  int items = 0;
+  ColsumParams C;
+  memset(&C, 0, sizeof(C));
+  C.d = d;
+  for (int p = 0; p < n_prob; ++p) {
+    if (!make_tmap_2d_f32(&P.tmX[p], pr[p].X, (uint64_t)pr[p].k, (uint64_t)pr[p].n, (uint64_t)pr[p].ldx * 4, 32, BK)) return 4;
+    if (!make_tmap_2d_f32(&P.tmG[p], pr[p].dY, (uint64_t)d, (uint64_t)pr[p].n, (uint64_t)pr[p].lddy * 4, 32, BK)) return 4;
+    WgProblem& w = P.prob[p];
+    w.n = (int)pr[p].n; w.k = pr[p].k; w.ft_tiles = (pr[p].k + BM - 1) / BM;
+    w.rows_per_chunk = wg_rows_per_chunk(pr[p].n);
+    w.chunks = (int)((pr[p].n + w.rows_per_chunk - 1) / w.rows_per_chunk);
+    w.item_start = items;
+    items += w.ft_tiles * w.chunks;
+    C.dY[p] = pr[p].dY; C.ld[p] = pr[p].lddy; C.n[p] = pr[p].n; C.db[p] = pr[p].db; C.acc[p] = pr[p].accumulate;
+  }
+  P.total_items = items;
+  const int64_t need = (int64_t)items * BM * d + (int64_t)n_prob * kColsumSlices * d;
+  LLMREC_CHECK_ARG(scratch && scratch_elems >= need, "proj_wgrad: scratch too small (%lld < %lld)", (long long)scratch_elems, (long long)need);
+  P.partial = scratch;
+  C.n_prob = n_prob; C.partial = scratch + (int64_t)items * BM * d;
+  uint32_t smem;
+  P.stages = stages_for(d, split, &smem);
+  P.tmem_cols = (int)pow2_cols(2 * d);
+  int grid = items < 148 ? items : 148;
+  if (grid <= 0) return 0;
+  if (split) {
+    cudaFuncSetAttribute(proj_wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    proj_wgrad_tc_kernel<true><<<grid, 384, smem, st>>>(P);
+  } else {
+    cudaFuncSetAttribute(proj_wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    proj_wgrad_tc_kernel<false><<<grid, 384, smem, st>>>(P);
+  }
+  LLMREC_CHECK_LAUNCH("proj_wgrad_tc");
+  for (int p = 0; p < n_prob; ++p) {
+    const WgProblem& w = P.prob[p];
+    wgrad_reduce_kernel<<<w.ft_tiles, 256, 0, st>>>(scratch, w.item_start, w.ft_tiles, w.chunks, w.k, d, pr[p].dW, pr[p].accumulate);
+    LLMREC_CHECK_LAUNCH("wgrad_reduce");
+  }
+  colsum_partial_kernel<<<dim3(kColsumSlices, n_prob), 256, 0, st>>>(C);
+  LLMREC_CHECK_LAUNCH("colsum_partial");
+  colsum_final_kernel<<<1, 256, 0, st>>>(C);
+  LLMREC_CHECK_LAUNCH("colsum_final");
+  return 0;
+}
+
+}  // namespace llmrec

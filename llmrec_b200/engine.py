@@ -131,12 +131,13 @@ class HotPath:
         d, L, S, m = self.d, self.L, self.S, self.cfg.proj_mode
         p, f = self.p, self.feats
         if self.has_feats:
-            with self._t("proj_fwd"):
-                ops.proj_fwd(f["image"], p["image_trans.weight"], p["image_trans.bias"], self.blk(self.Pi, 0), m)     # Models.py:145
-                ops.proj_fwd(f["text"], p["text_trans.weight"], p["text_trans.bias"], self.blk(self.Pi, 1), m)        # :146
-                for j, k in enumerate(self.keys):                                                                        # :148-150
-                    ops.proj_fwd(f["item"][k], p["item_trans.weight"], p["item_trans.bias"], self.blk(self.Pi, 2 + j), m)
-                ops.proj_fwd(f["user"], p["user_trans.weight"], p["user_trans.bias"], self.P_usr, m)                  # :147
+            with self._t("proj_fwd"):                                                                                # Models.py:145-150
+                probs = [(f["image"], p["image_trans.weight"], p["image_trans.bias"], self.blk(self.Pi, 0)),
+                         (f["text"], p["text_trans.weight"], p["text_trans.bias"], self.blk(self.Pi, 1))]
+                probs += [(f["item"][k], p["item_trans.weight"], p["item_trans.bias"], self.blk(self.Pi, 2 + j)) for j, k in enumerate(self.keys)]
+                probs.append((f["user"], p["user_trans.weight"], p["user_trans.bias"], self.P_usr))
+                probs.sort(key=lambda t: -t[0].shape[1])                       # long-K tiles first
+                ops.proj_fwd_group(probs, d, m)
         # step t even: ui (I_{t/2} -> U_{t/2+1});  t odd: iu (U_{(t+1)/2} -> I_{(t+1)/2}); softmax on the last layer
         n_steps = max(2 * L, 3 if self.has_feats else 0)
         for t in range(n_steps):
@@ -219,11 +220,11 @@ class HotPath:
         if self.has_feats:
             f, g = self.feats, self.grads
             with self._t("proj_wgrad"):
-                ops.proj_wgrad(f["image"], self.blk(self.GPi, 0), g["image_trans.weight"], g["image_trans.bias"], False, m)
-                ops.proj_wgrad(f["text"], self.blk(self.GPi, 1), g["text_trans.weight"], g["text_trans.bias"], False, m)
-                for j, k in enumerate(self.keys):
-                    ops.proj_wgrad(f["item"][k], self.blk(self.GPi, 2 + j), g["item_trans.weight"], g["item_trans.bias"], j > 0, m)
-                ops.proj_wgrad(f["user"], self.GP_usr, g["user_trans.weight"], g["user_trans.bias"], False, m)
+                probs = [(f["item"][k], self.blk(self.GPi, 2 + j), g["item_trans.weight"], g["item_trans.bias"], j > 0) for j, k in enumerate(self.keys)]
+                probs.append((f["user"], self.GP_usr, g["user_trans.weight"], g["user_trans.bias"], False))
+                probs.append((f["text"], self.blk(self.GPi, 1), g["text_trans.weight"], g["text_trans.bias"], False))
+                probs.append((f["image"], self.blk(self.GPi, 0), g["image_trans.weight"], g["image_trans.bias"], False))
+                ops.proj_wgrad_group(probs, d, m)
         return self.grads
 
     # ---- losses + their gradients w.r.t. the forward outputs ---------------------------------------------

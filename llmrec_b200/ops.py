@@ -133,38 +133,55 @@ def row_softmax_bwd(S, dS, out=None):
 PROJ_MODE = {"3xtf32": 0, "tf32": 1, "fp32": 2}
 
 
+_scratch = {}
+
+
+def _get_scratch(key, n, device):
+    t = _scratch.get(key)
+    if t is None or t.numel() < n:
+        t = _scratch[key] = torch.empty(max(int(n), 1), dtype=torch.float32, device=device)
+    return t
+
+
+def proj_fwd_group(problems, d, mode=0):
+    """problems: list of (X[n x k], W[d x k], bias[d]|None, out[n x d]).  One grouped launch (tcgen05) --
+    the 8 nn.Linear calls of Models.py:145-150.  Problems sharing W share the hi/lo split buffer."""
+    arr = (N.ProjFwdProblem * len(problems))()
+    for i, (X, W, b, out) in enumerate(problems):
+        _mat(X); _mat(out)
+        n, k = X.shape
+        if not W.is_contiguous() or tuple(W.shape) != (d, k) or tuple(out.shape) != (n, d):
+            raise ValueError("proj_fwd: bad shapes")
+        ws = _get_scratch(("wsplit", W.data_ptr()), 2 * d * k, X.device) if mode == 0 else None
+        arr[i] = N.ProjFwdProblem(_p(X), _p(W), _p(b), _p(out), _p(ws), _ld(X), _ld(out), n, k, 0)
+    N.check(N.lib().llmrec_proj_fwd_group_f32(arr, len(problems), d, mode, _stream()), "proj_fwd_group")
+    _count(1 + len({int(p.W) for p in arr}) if mode == 0 else 1)
+
+
 def proj_fwd(X, W, b, out, mode=0):
     """out[n x d] = X[n x k] W[d x k]^T + b  (nn.Linear; Models.py:145-150)."""
-    _mat(X); _mat(out)
-    n, k = X.shape
-    d = W.shape[0]
-    if not W.is_contiguous() or W.shape[1] != k or out.shape != (n, d):
-        raise ValueError("proj_fwd: bad shapes")
-    N.check(N.lib().llmrec_proj_fwd_f32(_p(X), _ld(X), _p(W), _p(b), _p(out), _ld(out), n, k, d, mode, _stream()), "proj_fwd")
-    _count()
+    proj_fwd_group([(X, W, b, out)], W.shape[0], mode)
     return out
 
 
-_wgrad_scratch = {}
+def proj_wgrad_group(problems, d, mode=0):
+    """problems: list of (X[n x k], dY[n x d], dW[d x k], db[d]|None, accumulate).  dW (+)= dY^T X ; db (+)= colsum(dY)."""
+    arr = (N.ProjWgradProblem * len(problems))()
+    for i, (X, dY, dW, db, acc) in enumerate(problems):
+        _mat(X); _mat(dY)
+        n, k = X.shape
+        if not dW.is_contiguous() or tuple(dW.shape) != (d, k) or tuple(dY.shape) != (n, d):
+            raise ValueError("proj_wgrad: bad shapes")
+        arr[i] = N.ProjWgradProblem(_p(X), _p(dY), _p(dW), _p(db), _ld(X), _ld(dY), n, k, 1 if acc else 0)
+    need = int(N.lib().llmrec_proj_wgrad_group_scratch(arr, len(problems), d, mode))
+    scratch = _get_scratch(("wgrad", problems[0][0].device.index), need, problems[0][0].device) if need else None
+    N.check(N.lib().llmrec_proj_wgrad_group_f32(arr, len(problems), d, mode, _p(scratch), need, _stream()), "proj_wgrad_group")
+    _count(3 + len(problems) if need else len(problems))
 
 
 def proj_wgrad(X, dY, dW, db, accumulate=False, mode=0):
     """dW[d x k] (+)= dY^T X ; db[d] (+)= colsum(dY)."""
-    _mat(X); _mat(dY)
-    n, k = X.shape
-    d = dY.shape[1]
-    need = int(N.lib().llmrec_proj_wgrad_scratch(n, k, d, mode))
-    scratch = None
-    if need:
-        key = (X.device.index, need)
-        scratch = _wgrad_scratch.get(key)
-        if scratch is None:
-            scratch = torch.empty(need, dtype=torch.float32, device=X.device)
-            _wgrad_scratch.clear()
-            _wgrad_scratch[key] = scratch
-    N.check(N.lib().llmrec_proj_wgrad_f32(_p(X), _ld(X), _p(dY), _ld(dY), _p(dW), _p(db), n, k, d, 1 if accumulate else 0, mode,
-                                           _p(scratch), need, _stream()), "proj_wgrad")
-    _count()
+    proj_wgrad_group([(X, dY, dW, db, accumulate)], dY.shape[1], mode)
 
 
 def _ptr_table(tensors):
