@@ -17,8 +17,9 @@
 // mbarriers, double-buffered TMEM accumulator with tmem_full/tmem_empty mbarriers.
 //
 // Layouts: forward operands are K-major 128-byte-swizzled tiles ([rows][32 fp32]); the wgrad contraction
-// runs over ROWS, so its operands are MN-major swizzled tiles ([32-column atom][32 rows][32 fp32]) fetched
-// as 32x32 TMA boxes -- no transpose pass over X or dY is ever materialised.
+// runs over ROWS, so its operands are MN-major tiles ([32-column atom][32 rows][32 fp32], 128B swizzle with
+// 32-byte atoms = UMMA layout SWIZZLE_128B_BASE32B / TMA SWIZZLE_128B_ATOM_32B, the one layout tcgen05 takes for
+// MN-major tf32) fetched as 32x32 TMA boxes -- no transpose pass over X or dY is ever materialised.
 #include <mutex>
 #include <vector>
 #include <string.h>
@@ -55,11 +56,11 @@ static EncodeFn get_encode() {
 }
 
 bool make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
-                      uint32_t box_inner, uint32_t box_outer) {
+                      uint32_t box_inner, uint32_t box_outer, bool swizzle32) {
   struct Entry { TmapKey k; CUtensorMap m; };
   static std::vector<Entry> cache;
   static std::mutex mu;
-  TmapKey key{base, inner, outer, row_stride_bytes, box_inner, box_outer};
+  TmapKey key{base, inner, outer, row_stride_bytes, box_inner, box_outer, swizzle32 ? 1u : 0u, 0u};
   std::lock_guard<std::mutex> lock(mu);
   for (auto& e : cache)
     if (memcmp(&e.k, &key, sizeof(key)) == 0) { *out = e.m; return true; }
@@ -70,7 +71,7 @@ bool make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t inner, uint64
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) inner=%llu outer=%llu stride=%llu box=%ux%u", (int)r,
                                      (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)row_stride_bytes, box_inner, box_outer); return false; }
@@ -343,13 +344,13 @@ __global__ void __launch_bounds__(384, 1) proj_wgrad_tc_kernel(const __grid_cons
         const uint32_t a0 = smem_u32(sA(st.stage)), al0 = smem_u32(sAlo(st.stage));
         const uint32_t b0 = smem_u32(sB(st.stage)), bl0 = smem_u32(sBlo(st.stage));
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {  // UMMA_K = 8 rows = one 8 x 128 B atom along K
-          const uint64_t ad = smem_desc_sw128(a0 + kk * 1024, 4096, 1024);
-          const uint64_t bd = smem_desc_sw128(b0 + kk * 1024, 4096, 1024);
+        for (int kk = 0; kk < 4; ++kk) {  // UMMA_K = 8 rows = two 4-row x 128 B atoms along K (SBO 512), MN atoms 4096 B apart (LBO)
+          const uint64_t ad = smem_desc_sw128(a0 + kk * 1024, 4096, 512, 1);
+          const uint64_t bd = smem_desc_sw128(b0 + kk * 1024, 4096, 512, 1);
           const uint32_t first = (kb | kk) != 0;
           if (SPLIT) {
-            const uint64_t ald = smem_desc_sw128(al0 + kk * 1024, 4096, 1024);
-            const uint64_t bld = smem_desc_sw128(bl0 + kk * 1024, 4096, 1024);
+            const uint64_t ald = smem_desc_sw128(al0 + kk * 1024, 4096, 512, 1);
+            const uint64_t bld = smem_desc_sw128(bl0 + kk * 1024, 4096, 512, 1);
             umma_tf32(d_tmem, ald, bd, idesc, first);
             umma_tf32(d_tmem, ad, bld, idesc, 1);
             umma_tf32(d_tmem, ad, bd, idesc, 1);
@@ -530,8 +531,8 @@ int proj_wgrad_tc_group(const llmrec_proj_wgrad_problem* pr, int n_prob, int d, 
   memset(&C, 0, sizeof(C));
   C.d = d;
   for (int p = 0; p < n_prob; ++p) {
-    if (!make_tmap_2d_f32(&P.tmX[p], pr[p].X, (uint64_t)pr[p].k, (uint64_t)pr[p].n, (uint64_t)pr[p].ldx * 4, 32, BK)) return 4;
-    if (!make_tmap_2d_f32(&P.tmG[p], pr[p].dY, (uint64_t)d, (uint64_t)pr[p].n, (uint64_t)pr[p].lddy * 4, 32, BK)) return 4;
+    if (!make_tmap_2d_f32(&P.tmX[p], pr[p].X, (uint64_t)pr[p].k, (uint64_t)pr[p].n, (uint64_t)pr[p].ldx * 4, 32, BK, true)) return 4;
+    if (!make_tmap_2d_f32(&P.tmG[p], pr[p].dY, (uint64_t)d, (uint64_t)pr[p].n, (uint64_t)pr[p].lddy * 4, 32, BK, true)) return 4;
     WgProblem& w = P.prob[p];
     w.n = (int)pr[p].n; w.k = pr[p].k; w.ft_tiles = (pr[p].k + BM - 1) / BM;
     w.rows_per_chunk = wg_rows_per_chunk(pr[p].n);

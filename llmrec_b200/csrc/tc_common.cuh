@@ -106,13 +106,16 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // ---- descriptors ------------------------------------------------------------------------------------
 // Shared-memory matrix descriptor (64-bit): [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1,
 // [49,52) base offset, [61,64) layout (2 = SWIZZLE_128B).  Tiles are 1024-byte aligned (base offset 0).
-__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// layout: 2 = SWIZZLE_128B (16-byte swizzle atoms; K-major tiles), 1 = SWIZZLE_128B_BASE32B (32-byte swizzle atoms,
+// 4-row K groups) -- the only shared-memory layout tcgen05 accepts for MN-major 32-bit (tf32) operands; TMA produces it
+// with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout = 2) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3fffu);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout << 61;
   return d;
 }
 // Instruction descriptor, kind::tf32 with fp32 accumulate: c_format[4,6)=1, a_format[7,10)=2, b_format[10,13)=2,
@@ -137,8 +140,9 @@ __device__ __forceinline__ void split_tile_inplace(float4* tile, float4* lo, int
 }  // namespace tc
 
 // ---- host side: tensor-map encoding through the driver entry point (no -lcuda link dependency) ----
-struct TmapKey { const void* base; uint64_t d0, d1, stride; uint32_t b0, b1; };
+struct TmapKey { const void* base; uint64_t d0, d1, stride; uint32_t b0, b1; uint32_t swz, pad; };
+// swizzle32: false -> CU_TENSOR_MAP_SWIZZLE_128B, true -> CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
 bool make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
-                      uint32_t box_inner, uint32_t box_outer);
+                      uint32_t box_inner, uint32_t box_outer, bool swizzle32 = false);
 
 }  // namespace llmrec
