@@ -130,7 +130,9 @@ def test_projection_and_wgrad(n, k, d):
     for mode in (0, 2):
         ops.proj_fwd(X, W, b, Y, mode)
         ref = (X.double() @ W.double().t() + b.double())
-        torch.testing.assert_close(Y.double(), ref, rtol=1e-5, atol=1e-5)
+        # mode 2: sequential fp32 FMA; mode 0: 3xTF32 products (2^-21) + tensor-core fp32 accumulation -> 1e-5-class
+        tol = 1e-5 if mode == 2 else 1e-4
+        torch.testing.assert_close(Y.double(), ref, rtol=tol, atol=tol)
         dY = torch.randn(n, 3 * d, generator=g).to(cuda)[:, d:2 * d]
         dW = torch.empty(d, k, device=cuda); db = torch.empty(d, device=cuda)
         ops.proj_wgrad(X, dY, dW, db, False, mode)
@@ -283,6 +285,7 @@ def test_score_topk_vs_oracle(nb, ni, d, K):
         scores = (U[users].double() @ I.double().t()).float().numpy()
         want = O.rank_users_numpy(scores, [train[u] for u in users.tolist()], K)
         got = idx.cpu().numpy().copy()
+        assert not any(set(got[r]) & set(train[u]) for r, u in enumerate(users.tolist()))     # train items never ranked
         for r, u in enumerate(users.tolist()):                 # fewer than K candidates: tail is -1 (the reference returns a shorter list)
             n_cand = ni - len(train[u])
             if n_cand < K:
@@ -294,7 +297,6 @@ def test_score_topk_vs_oracle(nb, ni, d, K):
             a, b = scores[r, got[r]], scores[r, want[r]]
             assert np.allclose(a, b, rtol=0, atol=2e-5), (r, got[r], want[r])
         assert same.mean() > 0.97
-        assert not any(set(got[r]) & set(train[u]) for r, u in enumerate(users.tolist()))
 
 
 def test_score_topk_exact_ties_lowest_id():
