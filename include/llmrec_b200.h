@@ -44,8 +44,9 @@ int llmrec_device_ok(void);
  * rs = (deg+1e-8)^-1/2 (main.py:114-126), so vals == NULL there.
  * seg flags: bit0 = row softmax over the d columns after scaling (Models.py:174-175); the optional
  * addend Z is added after the epilogue (used by the backward chain: g_out = g_direct + A^T g).
- * Optional row tiling (rows longer than tile_nnz are split over several warps and reduced by a
- * deterministic second pass): pass NULL for one warp per row.
+ * Work decomposition: `tiling` (required for the vectorised kernels; NULL falls back to the scalar
+ * warp-per-row kernel) lists nnz-bounded tiles so that low-degree rows are batched and power-law rows are
+ * split over several warps and reduced by a deterministic second pass.
  * --------------------------------------------------------------------------------------------- */
 typedef struct {
   const float* X;   /* gathered operand  [n_cols x d], leading dimension ldx */
@@ -59,13 +60,19 @@ typedef struct {
 } llmrec_spmm_seg;
 
 typedef struct {
-  const int32_t* tile_row;    /* [n_tiles] row of each tile; tiles of split rows are numbered first */
-  const int32_t* tile_beg;    /* [n_tiles] first nnz of the tile; end = min(beg+tile_nnz, row end) */
-  const int32_t* split_row;   /* [n_split] rows owning more than one tile */
-  const int32_t* split_first; /* [n_split+1] first tile of each split row (its tiles are consecutive) */
-  float* scratch;             /* [n_split_tiles * nseg * d] partial sums */
-  int32_t n_tiles, tile_nnz, n_split, n_split_tiles;
+  const int32_t* tiles;       /* [n_tiles][4] = {first row, #complete rows (0 = one piece of a long row), e0, e1};
+                                 pieces of long rows are numbered first (llmrec_spmm_plan_tiles builds this) */
+  const int32_t* split_row;   /* [n_split] rows that were cut into pieces */
+  const int32_t* split_first; /* [n_split+1] first piece (tile id) of each split row */
+  float* scratch;             /* [n_split_tiles * min(nseg,16) * d] partial sums of the pieces */
+  int32_t n_tiles, n_split, n_split_tiles, _pad;
 } llmrec_spmm_tiling;
+
+/* Host-side planner (runs once per graph): tiles of <= tile_nnz non-zeros, each a run of <= max_rows (<= 15)
+ * complete rows or one piece of a longer row.  Call with tiles_out == NULL to get the sizes in
+ * counts_out = {n_tiles, n_split, n_split_tiles}, allocate, call again.  All pointers are HOST memory. */
+int llmrec_spmm_plan_tiles(const int32_t* rowptr_host, int32_t n_rows, int32_t tile_nnz, int32_t max_rows,
+                           int32_t* tiles_out, int32_t* split_row_out, int32_t* split_first_out, int32_t* counts_out);
 
 #define LLMREC_SPMM_SOFTMAX 1
 

@@ -24,9 +24,8 @@ class SpmmSeg(C.Structure):
 
 
 class SpmmTiling(C.Structure):
-    _fields_ = [("tile_row", C.c_void_p), ("tile_beg", C.c_void_p), ("split_row", C.c_void_p), ("split_first", C.c_void_p),
-                ("scratch", C.c_void_p), ("n_tiles", C.c_int32), ("tile_nnz", C.c_int32), ("n_split", C.c_int32),
-                ("n_split_tiles", C.c_int32)]
+    _fields_ = [("tiles", C.c_void_p), ("split_row", C.c_void_p), ("split_first", C.c_void_p), ("scratch", C.c_void_p),
+                ("n_tiles", C.c_int32), ("n_split", C.c_int32), ("n_split_tiles", C.c_int32), ("_pad", C.c_int32)]
 
 
 class ProjFwdProblem(C.Structure):
@@ -52,6 +51,7 @@ SIGNATURES = {
     "llmrec_device_ok": (C.c_int, []),
     "llmrec_spmm_csr_f32": (C.c_int, [c_i32p, c_i32p, c_f32p, c_f32p, c_f32p, C.c_int32, C.c_int32, C.c_int32,
                                       C.POINTER(SpmmSeg), C.c_int32, C.POINTER(SpmmTiling), c_stream]),
+    "llmrec_spmm_plan_tiles": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "llmrec_row_softmax_f32": (C.c_int, [c_f32p, C.c_int64, c_f32p, C.c_int64, C.c_int64, C.c_int32, c_stream]),
     "llmrec_row_softmax_bwd_f32": (C.c_int, [c_f32p, C.c_int64, c_f32p, C.c_int64, c_f32p, C.c_int64, C.c_int64, C.c_int32, c_stream]),
     "llmrec_proj_fwd_f32": (C.c_int, [c_f32p, C.c_int64, c_f32p, c_f32p, c_f32p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, c_f32p, c_stream]),

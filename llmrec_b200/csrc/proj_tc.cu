@@ -405,20 +405,38 @@ __global__ void __launch_bounds__(384, 1) proj_wgrad_tc_kernel(const __grid_cons
   if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols); }
 }
 
-// dW[dc][f] (+)= sum over row chunks of partial[item][f % 128][dc]   (fixed order -> deterministic)
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int item_start, int ft_tiles, int chunks,
-                                                           int k, int d, float* __restrict__ dW, int accumulate) {
-  const int ft = blockIdx.x;
-  for (int i = threadIdx.x; i < BM * d; i += blockDim.x) {
+// dW[dc][f] = sum over (problems sharing this dW, in list order) x (row chunks, in order) of partial[item][f % 128][dc]
+// One launch for every output: block = (output feature tile, 32-feature quarter); fixed summation order -> deterministic.
+struct ReduceOut { float* dW; int k, n_src, accumulate, blk_start; int src[kMaxProb]; };
+struct ReduceParams { ReduceOut out[kMaxProb]; int n_out; int d; const float* partial; WgProblem prob[kMaxProb]; };
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const ReduceParams R) {
+  __shared__ float tile[32][257];  // [f][dc] padded
+  int o = 0;
+  while (o + 1 < R.n_out && (int)blockIdx.x >= R.out[o + 1].blk_start) ++o;
+  const ReduceOut ro = R.out[o];
+  const int local = blockIdx.x - ro.blk_start;
+  const int ft = local >> 2, q = local & 3, d = R.d;
+  for (int i = threadIdx.x; i < 32 * d; i += blockDim.x) {
     const int f = i / d, dc = i - f * d;
-    const int gf = ft * BM + f;
-    if (gf >= k) continue;
     float s = 0.f;
-    for (int c = 0; c < chunks; ++c) s += partial[((long long)(item_start + c * ft_tiles + ft) * BM + f) * d + dc];
-    float* o = dW + (long long)dc * k + gf;
-    *o = accumulate ? (*o + s) : s;
+    for (int j = 0; j < ro.n_src; ++j) {
+      const WgProblem pr = R.prob[ro.src[j]];
+      for (int c = 0; c < pr.chunks; ++c)
+        s += R.partial[((long long)(pr.item_start + c * pr.ft_tiles + ft) * BM + q * 32 + f) * d + dc];
+    }
+    tile[f][dc] = s;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * d; i += blockDim.x) {
+    const int dc = i >> 5, f = i & 31;
+    const int gf = ft * BM + q * 32 + f;
+    if (gf < ro.k) {
+      float* p = ro.dW + (long long)dc * ro.k + gf;
+      *p = ro.accumulate ? (*p + tile[f][dc]) : tile[f][dc];
+    }
   }
 }
+
 // db[dc] (+)= sum_r dY[r][dc] : 16 row-slices per problem -> partial, then an ordered combine (deterministic;
 // problems sharing one db -- the 5 attribute matrices behind item_trans -- accumulate in problem order)
 struct ColsumParams { const float* dY[kMaxProb]; long long ld[kMaxProb]; long long n[kMaxProb]; float* db[kMaxProb]; int acc[kMaxProb]; int d; int n_prob; float* partial; };
@@ -559,11 +577,24 @@ int proj_wgrad_tc_group(const llmrec_proj_wgrad_problem* pr, int n_prob, int d, 
     proj_wgrad_tc_kernel<false><<<grid, 384, smem, st>>>(P);
   }
   LLMREC_CHECK_LAUNCH("proj_wgrad_tc");
+  ReduceParams R;
+  memset(&R, 0, sizeof(R));
+  R.d = d; R.partial = scratch;
+  int blocks = 0;
   for (int p = 0; p < n_prob; ++p) {
-    const WgProblem& w = P.prob[p];
-    wgrad_reduce_kernel<<<w.ft_tiles, 256, 0, st>>>(scratch, w.item_start, w.ft_tiles, w.chunks, w.k, d, pr[p].dW, pr[p].accumulate);
-    LLMREC_CHECK_LAUNCH("wgrad_reduce");
+    R.prob[p] = P.prob[p];
+    int o = -1;
+    for (int q = 0; q < R.n_out; ++q) if (R.out[q].dW == pr[p].dW) o = q;
+    if (o < 0) {
+      o = R.n_out++;
+      R.out[o].dW = pr[p].dW; R.out[o].k = pr[p].k; R.out[o].accumulate = pr[p].accumulate; R.out[o].n_src = 0;
+    }
+    LLMREC_CHECK_ARG(R.out[o].k == pr[p].k, "proj_wgrad: problems sharing dW must share k");
+    R.out[o].src[R.out[o].n_src++] = p;
   }
+  for (int o = 0; o < R.n_out; ++o) { R.out[o].blk_start = blocks; blocks += ((R.out[o].k + BM - 1) / BM) * 4; }
+  wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(R);
+  LLMREC_CHECK_LAUNCH("wgrad_reduce");
   colsum_partial_kernel<<<dim3(kColsumSlices, n_prob), 256, 0, st>>>(C);
   LLMREC_CHECK_LAUNCH("colsum_partial");
   colsum_final_kernel<<<1, 256, 0, st>>>(C);

@@ -1,27 +1,31 @@
 // Propagation SpMM over a CSR pattern with row/column scaling (Models.py:57-61,152-183).
 //
-//   Y_s[r,:] (+)= epi( rs[r] * sum_{e in row r} v[e] * cs[col[e]] * X_s[col[e],:] )
+//   Y_s[r,:] = epi( rs[r] * sum_{e in row r} v[e] * cs[col[e]] * X_s[col[e],:] ) + Z_s[r,:]
 //
-// HBM-bound gather.  Design (sm_100a, no tensor cores -- this is index/byte work):
-//   * CSR-row-tiled: one warp (or sub-warp for narrow operands) owns a (row, [beg,end)) tile; rows
-//     longer than tile_nnz are split over several warps and reduced by a deterministic second pass.
-//   * the index stream (col, v, cs) is read once, coalesced, 32 entries per warp step and broadcast
-//     with warp shuffles; every dense operand sharing the pattern ("segment") is gathered in the same
-//     pass, so the 20 reference SpMMs per forward collapse to 4 launches.
-//   * each lane owns up to CH 16-byte column chunks of the concatenated segment row and keeps the
-//     partial sums in registers; neighbour rows are fetched with 128-bit read-only loads, 4 x CH in
-//     flight per lane (unrolled), which is what hides the gather latency.
-//   * scale, optional row-softmax over a segment's d columns (sub-warp shuffle reduction) and
-//     optional accumulate are fused into the store.
+// HBM/L2-bound gather -- index and byte work, no tensor cores.  Design (sm_100a):
+//   * CSR-row-TILED and nnz-flattened: the host plans tiles of <= tile_nnz non-zeros (llmrec_spmm_plan_tiles):
+//     a tile is either a run of up to 15 consecutive complete rows, or one piece of a long row.  One
+//     lane-group (8/16/32 lanes, by operand width) owns a tile: ONE coalesced read of the tile's row
+//     pointers, ONE coalesced read of its (col, v, cs) stream, then the gathers of ALL its rows are issued
+//     back to back, U at a time -- the dependent-load chain per row (rowptr -> col -> X) that makes
+//     warp-per-row kernels latency-bound on low-degree graphs is paid once per tile, and power-law rows
+//     no longer serialise on one warp.  Long-row pieces write raw partial sums; a second pass adds them
+//     in fixed order (deterministic, no atomics).
+//   * every dense operand sharing the pattern ("segment") is gathered in the same pass, so the index
+//     stream is read once for the image/text/attribute/profile/ID operands: the reference's 20 forward
+//     SpMMs are 4 launches.  Wide concatenations are cut into column windows over blockIdx.y so that
+//     each lane keeps at most CH 16-byte chunks (more warps in flight, fewer registers).
+//   * neighbour rows come in with 128-bit read-only loads, U x CH in flight per lane; row scale,
+//     optional row-softmax over a segment's d columns (lane-group shuffle reduction), optional addend
+//     and the store are fused at the row boundary.
 #include "common.cuh"
 
 namespace llmrec {
 
 struct SpmmParams {
   const int* rowptr; const int* col; const float* vals; const float* rs; const float* cs;
-  int n_rows; int d; int nseg; int f4_per_seg; int total_f4;
-  // tiling (n_tiles == 0 -> one work item per row)
-  const int* tile_row; const int* tile_beg; int n_tiles; int tile_nnz; int n_split_tiles; float* scratch;
+  int n_rows; int d; int nseg; int f4_per_seg; int total_f4; int any_softmax;
+  const int4* tiles; int n_tiles; int n_split_tiles; float* scratch;
   const int* split_row; const int* split_first; int n_split;
   llmrec_spmm_seg seg[LLMREC_MAX_SEG];
 };
@@ -37,10 +41,10 @@ struct LaneChunks {
 };
 
 template <int LPR, int CH>
-__device__ __forceinline__ void setup_chunks(const SpmmParams& p, int lane_in, LaneChunks<CH>& lc) {
+__device__ __forceinline__ void setup_chunks(const SpmmParams& p, int q0, int lane_in, LaneChunks<CH>& lc) {
 #pragma unroll
   for (int c = 0; c < CH; ++c) {
-    int q = c * LPR + lane_in;
+    int q = q0 + c * LPR + lane_in;
     bool on = q < p.total_f4;
     int s = on ? q / p.f4_per_seg : 0;
     int off = on ? (q - s * p.f4_per_seg) * 4 : 0;
@@ -55,125 +59,130 @@ __device__ __forceinline__ void setup_chunks(const SpmmParams& p, int lane_in, L
   }
 }
 
-// scale + (softmax) + (accumulate) + store for one output row
-template <int LPR, int CH>
-__device__ __forceinline__ void finish_row(const SpmmParams& p, const LaneChunks<CH>& lc, float4 (&acc)[CH], int row, bool valid) {
-  float s = (p.rs != nullptr && valid) ? p.rs[row] : 1.0f;
-  const int G = p.f4_per_seg;  // lanes per segment (power of two when any softmax flag is set)
+// scale + (softmax) + (addend) + store for one output row; only the lanes of `gmask` take part
+template <int CH>
+__device__ __forceinline__ void finish_row(const SpmmParams& p, const LaneChunks<CH>& lc, float4 (&acc)[CH], int row, unsigned gmask) {
+  const float s = p.rs ? __ldg(p.rs + row) : 1.0f;
+  const int G = p.f4_per_seg;  // lanes per segment (power of two <= group size whenever a softmax flag is set)
 #pragma unroll
   for (int c = 0; c < CH; ++c) {
     float4 a = acc[c];
     a.x *= s; a.y *= s; a.z *= s; a.w *= s;
-    // softmax is warp-uniform per launch group decision: all lanes run the shuffles
-    bool any_sm = __any_sync(0xffffffffu, (lc.flags[c] & LLMREC_SPMM_SOFTMAX) != 0);
-    if (any_sm) {
+    if (p.any_softmax) {  // launch-uniform: every lane of the group runs the shuffles
       float m = fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w));
-      for (int o = G >> 1; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      for (int o = G >> 1; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(gmask, m, o));
       float4 e = make_float4(expf(a.x - m), expf(a.y - m), expf(a.z - m), expf(a.w - m));
       float t = (e.x + e.y) + (e.z + e.w);
-      for (int o = G >> 1; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      for (int o = G >> 1; o > 0; o >>= 1) t += __shfl_xor_sync(gmask, t, o);
       if (lc.flags[c] & LLMREC_SPMM_SOFTMAX) {
         float inv = 1.0f / t;
         a = make_float4(e.x * inv, e.y * inv, e.z * inv, e.w * inv);
       }
     }
-    if (valid && lc.on[c]) {
-      float* y = lc.yb[c] + (int64_t)row * lc.ldy[c];
+    if (lc.on[c]) {
       if (lc.zb[c]) {
         float4 o = *reinterpret_cast<const float4*>(lc.zb[c] + (int64_t)row * lc.ldz[c]);
         a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
       }
-      st4(y, a);
+      st4(lc.yb[c] + (int64_t)row * lc.ldy[c], a);
     }
+    acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
-template <int LPR, int CH>
-__global__ void __launch_bounds__(256) spmm_kernel(const SpmmParams p) {
-  constexpr int RPW = 32 / LPR;  // work items per warp
+template <int LPR, int CH, int U>
+__global__ void __launch_bounds__(256) spmm_tile_kernel(const SpmmParams p) {
+  constexpr int RPW = 32 / LPR;  // tiles per warp
   const int lane = threadIdx.x & 31;
   const int lane_in = lane % LPR;
   const int sub = lane / LPR;
-  const int warp_global = (blockIdx.x * (blockDim.x >> 5)) + (threadIdx.x >> 5);
-  const int n_items = p.n_tiles > 0 ? p.n_tiles : p.n_rows;
-  const int item = warp_global * RPW + sub;
-  if (warp_global * RPW >= n_items) return;  // whole warp idle
-  const bool valid = item < n_items;
+  const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
+  const int tile = ((blockIdx.x * (blockDim.x >> 5)) + (threadIdx.x >> 5)) * RPW + sub;
+  if (tile >= p.n_tiles) return;  // whole lane-group leaves together
 
   LaneChunks<CH> lc;
-  setup_chunks<LPR, CH>(p, lane_in, lc);
+  setup_chunks<LPR, CH>(p, blockIdx.y * (LPR * CH), lane_in, lc);
 
-  int row = 0, beg = 0, end = 0;
-  bool whole = true;
-  if (valid) {
-    if (p.n_tiles > 0) {
-      row = p.tile_row[item];
-      beg = p.tile_beg[item];
-      int rend = p.rowptr[row + 1];
-      end = min(beg + p.tile_nnz, rend);
-      whole = (beg == p.rowptr[row]) && (end == rend);
-    } else {
-      row = item;
-      beg = p.rowptr[row];
-      end = p.rowptr[row + 1];
-    }
+  const int4 t = __ldg(p.tiles + tile);  // {first row, #complete rows (0 = piece of a long row), e0, e1}
+  const int row0 = t.x, nrows = t.y, e0 = t.z, e1 = t.w;
+  const bool piece = nrows == 0;
+  // row pointers of the tile: entries 0..nrows live in two registers per lane (nrows <= 15 <= 2*LPR-1)
+  int rp_lo = 0x7fffffff, rp_hi = 0x7fffffff;
+  if (!piece) {
+    if (lane_in <= nrows) rp_lo = __ldg(p.rowptr + row0 + lane_in);
+    if (LPR < 16 && LPR + lane_in <= nrows) rp_hi = __ldg(p.rowptr + row0 + LPR + lane_in);
   }
-  int len = end - beg;
-  int maxlen = len;
-  if (RPW > 1) {
-#pragma unroll
-    for (int o = 16; o >= LPR; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
-  }
+  auto row_end_of = [&](int i) -> int {  // end offset of local row i-1 == rowptr[row0 + i]
+    int lo = __shfl_sync(gmask, rp_lo, i & (LPR - 1), LPR);
+    int hi = __shfl_sync(gmask, rp_hi, i & (LPR - 1), LPR);
+    return (LPR < 16 && i >= LPR) ? hi : lo;
+  };
+  int cur = 0;
+  int row_end = piece ? e1 : row_end_of(1);
 
   float4 acc[CH];
 #pragma unroll
   for (int c = 0; c < CH; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  for (int k0 = 0; k0 < maxlen; k0 += LPR) {
-    int e = beg + k0 + lane_in;
+  const int len = e1 - e0;
+  for (int k0 = 0; k0 < len; k0 += LPR) {
+    const int e = e0 + k0 + lane_in;
     int cidx = 0;
     float w = 0.f;
-    if (e < end) {
+    if (e < e1) {
       cidx = __ldg(p.col + e);
       w = p.vals ? __ldg(p.vals + e) : 1.0f;
       if (p.cs) w *= __ldg(p.cs + cidx);
     }
-    int cnt = min(LPR, maxlen - k0);
-#pragma unroll 4
-    for (int j = 0; j < cnt; ++j) {
-      int cj = __shfl_sync(0xffffffffu, cidx, j, LPR);
-      float wj = __shfl_sync(0xffffffffu, w, j, LPR);
-      if (k0 + j < len) {
+    const int cnt = min(LPR, len - k0);
+    for (int j0 = 0; j0 < cnt; j0 += U) {
+      float4 x[U][CH];
+      float wj[U];
 #pragma unroll
-        for (int c = 0; c < CH; ++c) {
-          if (lc.on[c]) fma4(acc[c], wj, ldg4(lc.xb[c] + (int64_t)cj * lc.ldx[c]));
+      for (int u = 0; u < U; ++u) {
+        const int jj = (j0 + u) & (LPR - 1);
+        const int cj = __shfl_sync(gmask, cidx, jj, LPR);
+        wj[u] = __shfl_sync(gmask, w, jj, LPR);
+        const bool live = j0 + u < cnt;
+#pragma unroll
+        for (int c = 0; c < CH; ++c)
+          x[u][c] = (live && lc.on[c]) ? ldg4(lc.xb[c] + (int64_t)cj * lc.ldx[c]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (j0 + u < cnt) {
+          const int ge = e0 + k0 + j0 + u;
+          while (!piece && ge >= row_end) {  // row boundary (group-uniform); also steps over empty rows
+            finish_row<CH>(p, lc, acc, row0 + cur, gmask);
+            ++cur;
+            row_end = row_end_of(cur + 1);
+          }
+#pragma unroll
+          for (int c = 0; c < CH; ++c) fma4(acc[c], wj[u], x[u][c]);
         }
       }
     }
   }
-
-  if (whole) {
-    finish_row<LPR, CH>(p, lc, acc, row, valid);
-  } else {
-    // partial tile of a split row: raw sums to scratch (tiles of split rows are numbered first)
+  if (piece) {
+    // raw partial sums of one piece of a long row (pieces are numbered first: slot == tile id)
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
-      int q = c * LPR + lane_in;
-      if (q < p.total_f4) st4(p.scratch + ((int64_t)item * p.total_f4 + q) * 4, acc[c]);
+      const int q = blockIdx.y * (LPR * CH) + c * LPR + lane_in;
+      if (q < p.total_f4) st4(p.scratch + ((int64_t)tile * p.total_f4 + q) * 4, acc[c]);
     }
-    // keep warp-collective softmax shuffles of other sub-groups safe: nothing to do, finish_row
-    // is only entered by sub-groups with whole rows; with RPW>1 splitting is disabled on the host.
+  } else {
+    for (; cur < nrows; ++cur) finish_row<CH>(p, lc, acc, row0 + cur, gmask);  // last row and trailing empty rows
   }
 }
 
-// second pass for split rows: ordered sum of the tile partials, then the fused epilogue
+// second pass for long rows: ordered sum of the piece partials, then the fused epilogue (one warp per row and window)
 template <int CH>
 __global__ void __launch_bounds__(256) spmm_finish_kernel(const SpmmParams p) {
   const int lane = threadIdx.x & 31;
   const int w = (blockIdx.x * (blockDim.x >> 5)) + (threadIdx.x >> 5);
   if (w >= p.n_split) return;
   LaneChunks<CH> lc;
-  setup_chunks<32, CH>(p, lane, lc);
+  setup_chunks<32, CH>(p, blockIdx.y * (32 * CH), lane, lc);
   const int row = p.split_row[w];
   const int t0 = p.split_first[w], t1 = p.split_first[w + 1];
   float4 acc[CH];
@@ -182,14 +191,14 @@ __global__ void __launch_bounds__(256) spmm_finish_kernel(const SpmmParams p) {
   for (int t = t0; t < t1; ++t) {
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
-      int q = c * 32 + lane;
+      const int q = blockIdx.y * (32 * CH) + c * 32 + lane;
       if (q < p.total_f4) {
         float4 v = *reinterpret_cast<const float4*>(p.scratch + ((int64_t)t * p.total_f4 + q) * 4);
         acc[c].x += v.x; acc[c].y += v.y; acc[c].z += v.z; acc[c].w += v.w;
       }
     }
   }
-  finish_row<32, CH>(p, lc, acc, row, true);
+  finish_row<CH>(p, lc, acc, row, 0xffffffffu);
 }
 
 // generic scalar path: any d (not a multiple of 4, or unaligned operands); one warp per row
@@ -202,7 +211,6 @@ __global__ void spmm_scalar_kernel(const SpmmParams p) {
   for (int sgi = 0; sgi < p.nseg; ++sgi) {
     const llmrec_spmm_seg sg = p.seg[sgi];
     float m = -INFINITY;
-    // pass 1: values (kept in Y), track max for softmax
     for (int j = lane; j < p.d; j += 32) {
       float a = 0.f;
       for (int e = beg; e < end; ++e) {
@@ -239,19 +247,18 @@ __global__ void spmm_scalar_kernel(const SpmmParams p) {
   }
 }
 
-template <int LPR, int CH>
+template <int LPR, int CH, int U>
 static int launch_spmm(const SpmmParams& p, cudaStream_t st) {
   constexpr int RPW = 32 / LPR;
-  const int n_items = p.n_tiles > 0 ? p.n_tiles : p.n_rows;
-  const int warps = (n_items + RPW - 1) / RPW;
+  const int warps = (p.n_tiles + RPW - 1) / RPW;
   const int blocks = (warps + 7) / 8;
-  if (blocks > 0) spmm_kernel<LPR, CH><<<blocks, 256, 0, st>>>(p);
-  LLMREC_CHECK_LAUNCH("spmm");
+  const int windows = (p.total_f4 + LPR * CH - 1) / (LPR * CH);
+  if (blocks > 0) spmm_tile_kernel<LPR, CH, U><<<dim3(blocks, windows), 256, 0, st>>>(p);
+  LLMREC_CHECK_LAUNCH("spmm_tile");
   if (p.n_split > 0) {
-    if constexpr (LPR == 32) {
-      spmm_finish_kernel<CH><<<(p.n_split + 7) / 8, 256, 0, st>>>(p);
-      LLMREC_CHECK_LAUNCH("spmm_finish");
-    }
+    const int fw = (p.total_f4 + 32 * CH - 1) / (32 * CH);
+    spmm_finish_kernel<CH><<<dim3((p.n_split + 7) / 8, fw), 256, 0, st>>>(p);
+    LLMREC_CHECK_LAUNCH("spmm_finish");
   }
   return 0;
 }
@@ -259,6 +266,56 @@ static int launch_spmm(const SpmmParams& p, cudaStream_t st) {
 }  // namespace llmrec
 
 using namespace llmrec;
+
+// Host-side tile planner (native graph-builder step).  Tiles are int32x4 {row0, nrows, e0, e1}; pieces of
+// long rows (nrows == 0) come first.  Call with tiles_out == NULL to size the outputs:
+// counts_out = {n_tiles, n_split, n_split_tiles}.
+extern "C" int llmrec_spmm_plan_tiles(const int32_t* rowptr_host, int32_t n_rows, int32_t tile_nnz, int32_t max_rows,
+                                      int32_t* tiles_out, int32_t* split_row_out, int32_t* split_first_out, int32_t* counts_out) {
+  LLMREC_CHECK_ARG(tile_nnz >= 8 && max_rows >= 1 && max_rows <= 15, "spmm_plan: tile_nnz=%d max_rows=%d out of range", tile_nnz, max_rows);
+  int64_t n_split = 0, n_pieces = 0, n_groups = 0;
+  // pass 1: pieces
+  for (int32_t r = 0; r < n_rows; ++r) {
+    const int32_t deg = rowptr_host[r + 1] - rowptr_host[r];
+    if (deg > tile_nnz) {
+      if (tiles_out) {
+        split_row_out[n_split] = r;
+        split_first_out[n_split] = (int32_t)n_pieces;
+        for (int32_t b = rowptr_host[r]; b < rowptr_host[r + 1]; b += tile_nnz) {
+          int32_t* t = tiles_out + 4 * n_pieces++;
+          t[0] = r; t[1] = 0; t[2] = b; t[3] = b + tile_nnz < rowptr_host[r + 1] ? b + tile_nnz : rowptr_host[r + 1];
+        }
+      } else {
+        n_pieces += (deg + tile_nnz - 1) / tile_nnz;
+      }
+      ++n_split;
+    }
+  }
+  if (tiles_out) split_first_out[n_split] = (int32_t)n_pieces;
+  // pass 2: groups of consecutive complete rows
+  int32_t r = 0;
+  while (r < n_rows) {
+    const int32_t deg0 = rowptr_host[r + 1] - rowptr_host[r];
+    if (deg0 > tile_nnz) { ++r; continue; }
+    int32_t r1 = r + 1;
+    while (r1 < n_rows && r1 - r < max_rows) {
+      const int32_t dn = rowptr_host[r1 + 1] - rowptr_host[r1];
+      if (dn > tile_nnz || rowptr_host[r1 + 1] - rowptr_host[r] > tile_nnz) break;
+      ++r1;
+    }
+    if (tiles_out) {
+      int32_t* t = tiles_out + 4 * (n_pieces + n_groups);
+      t[0] = r; t[1] = r1 - r; t[2] = rowptr_host[r]; t[3] = rowptr_host[r1];
+    }
+    ++n_groups;
+    r = r1;
+  }
+  LLMREC_CHECK_ARG(n_pieces + n_groups < 0x7fffffff, "spmm_plan: too many tiles");
+  counts_out[0] = (int32_t)(n_pieces + n_groups);
+  counts_out[1] = (int32_t)n_split;
+  counts_out[2] = (int32_t)n_pieces;
+  return 0;
+}
 
 extern "C" int llmrec_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, const float* vals,
                                    const float* row_scale, const float* col_scale,
@@ -271,7 +328,7 @@ extern "C" int llmrec_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, co
   if (n_rows == 0) return 0;
   cudaStream_t st = as_stream(stream);
 
-  bool vec_ok = (d % 4 == 0);
+  bool vec_ok = (d % 4 == 0) && tiling != nullptr && tiling->n_tiles > 0;
   bool any_softmax = false;
   for (int s = 0; s < nseg; ++s) {
     vec_ok = vec_ok && aligned16(segs[s].X) && aligned16(segs[s].Y) && segs[s].ldx % 4 == 0 && segs[s].ldy % 4 == 0 &&
@@ -294,40 +351,21 @@ extern "C" int llmrec_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, co
     return 0;
   }
 
-  // group segments so one launch covers at most 8 chunks per lane (256 float4) and MAX_SEG segments
-  int max_seg = 256 / f4;
-  if (max_seg < 1) max_seg = 1;
-  if (max_seg > LLMREC_MAX_SEG) max_seg = LLMREC_MAX_SEG;
-  LLMREC_CHECK_ARG(f4 <= 256, "spmm: d=%d too wide (max 1024)", d);
-  for (int s0 = 0; s0 < nseg; s0 += max_seg) {
+  for (int s0 = 0; s0 < nseg; s0 += LLMREC_MAX_SEG) {
     SpmmParams p{};
     p.rowptr = rowptr; p.col = col; p.vals = vals; p.rs = row_scale; p.cs = col_scale;
-    p.n_rows = n_rows; p.d = d; p.nseg = min(nseg - s0, max_seg);
-    p.f4_per_seg = f4; p.total_f4 = f4 * p.nseg;
+    p.n_rows = n_rows; p.d = d; p.nseg = min(nseg - s0, LLMREC_MAX_SEG);
+    p.f4_per_seg = f4; p.total_f4 = f4 * p.nseg; p.any_softmax = any_softmax ? 1 : 0;
     for (int s = 0; s < p.nseg; ++s) p.seg[s] = segs[s0 + s];
-    const bool narrow = p.total_f4 <= 16 && pow2;
-    if (tiling && tiling->n_tiles > 0 && !narrow) {
-      p.tile_row = tiling->tile_row; p.tile_beg = tiling->tile_beg; p.n_tiles = tiling->n_tiles;
-      p.tile_nnz = tiling->tile_nnz; p.n_split_tiles = tiling->n_split_tiles; p.scratch = tiling->scratch;
-      p.split_row = tiling->split_row; p.split_first = tiling->split_first; p.n_split = tiling->n_split;
-      LLMREC_CHECK_ARG(p.n_split == 0 || p.scratch != nullptr, "spmm: tiling with split rows needs scratch");
-    }
+    p.tiles = reinterpret_cast<const int4*>(tiling->tiles); p.n_tiles = tiling->n_tiles;
+    p.n_split_tiles = tiling->n_split_tiles; p.scratch = tiling->scratch;
+    p.split_row = tiling->split_row; p.split_first = tiling->split_first; p.n_split = tiling->n_split;
+    LLMREC_CHECK_ARG(p.n_split == 0 || p.scratch != nullptr, "spmm: long-row pieces need the scratch buffer");
     int rc = 0;
-    if (narrow && p.total_f4 <= 8) rc = launch_spmm<8, 1>(p, st);
-    else if (narrow) rc = launch_spmm<16, 1>(p, st);
-    else {
-      int ch = (p.total_f4 + 31) / 32;
-      switch (ch) {
-        case 1: rc = launch_spmm<32, 1>(p, st); break;
-        case 2: rc = launch_spmm<32, 2>(p, st); break;
-        case 3: rc = launch_spmm<32, 3>(p, st); break;
-        case 4: rc = launch_spmm<32, 4>(p, st); break;
-        case 5: rc = launch_spmm<32, 5>(p, st); break;
-        case 6: rc = launch_spmm<32, 6>(p, st); break;
-        case 7: rc = launch_spmm<32, 7>(p, st); break;
-        default: rc = launch_spmm<32, 8>(p, st); break;
-      }
-    }
+    if (p.total_f4 <= 8) rc = launch_spmm<8, 1, 4>(p, st);
+    else if (p.total_f4 <= 16) rc = launch_spmm<16, 1, 4>(p, st);
+    else if (p.total_f4 <= 32) rc = launch_spmm<32, 1, 8>(p, st);
+    else rc = launch_spmm<32, 2, 4>(p, st);
     if (rc) return rc;
   }
   return 0;

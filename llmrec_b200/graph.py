@@ -51,8 +51,8 @@ class BipartiteGraph:
         nu, ni = self.n_users, self.n_items
         self.ui = CsrOperator(self.rowptr_u, self.col_u, nu, ni, rs=self.su, tile_nnz=tile_nnz)
         self.iu = CsrOperator(self.rowptr_i, self.col_i, ni, nu, rs=self.si, tile_nnz=tile_nnz)
-        self.uiT = CsrOperator(self.rowptr_i, self.col_i, ni, nu, cs=self.su, tile_nnz=tile_nnz)
-        self.iuT = CsrOperator(self.rowptr_u, self.col_u, nu, ni, cs=self.si, tile_nnz=tile_nnz)
+        self.uiT = CsrOperator(self.rowptr_i, self.col_i, ni, nu, cs=self.su, plan=self.iu.plan)     # same pattern, same tiles
+        self.iuT = CsrOperator(self.rowptr_u, self.col_u, nu, ni, cs=self.si, plan=self.ui.plan)
         self.device = dev
 
     # the reference-facing COO tensors (what Trainer.ui_graph / iu_graph hold; main.py:128-134)

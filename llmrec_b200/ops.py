@@ -7,7 +7,9 @@ launches of the hand-written sm_100a kernels.  2-D operands must be row-major vi
 from __future__ import annotations
 
 import ctypes as C
+import os
 
+import numpy as np
 import torch
 
 from . import _native as N
@@ -44,56 +46,46 @@ def _i32(t, name="index"):
     return t
 
 
+DEFAULT_TILE_NNZ = int(os.environ.get("LLMREC_SPMM_TILE", "64"))
+
+
+class TilePlan:
+    """nnz-bounded work decomposition of a CSR pattern (llmrec_spmm_plan_tiles); shared by the operators
+    that use the same pattern (forward of one direction, backward of the other)."""
+
+    def __init__(self, rowptr_dev, n_rows, tile_nnz=0, max_rows=15):
+        tile_nnz = int(tile_nnz) or DEFAULT_TILE_NNZ
+        rp = np.ascontiguousarray(rowptr_dev.cpu().numpy().astype(np.int32))
+        lib = N.lib()
+        counts = np.zeros(3, dtype=np.int32)
+        N.check(lib.llmrec_spmm_plan_tiles(rp.ctypes.data, n_rows, tile_nnz, max_rows, None, None, None, counts.ctypes.data), "spmm_plan")
+        tiles = np.zeros((max(int(counts[0]), 1), 4), dtype=np.int32)
+        srow = np.zeros(max(int(counts[1]), 1), dtype=np.int32)
+        sfirst = np.zeros(int(counts[1]) + 1, dtype=np.int32)
+        N.check(lib.llmrec_spmm_plan_tiles(rp.ctypes.data, n_rows, tile_nnz, max_rows, tiles.ctypes.data, srow.ctypes.data,
+                                           sfirst.ctypes.data, counts.ctypes.data), "spmm_plan")
+        dev = rowptr_dev.device
+        self.tiles, self.split_row, self.split_first = (torch.from_numpy(a).to(dev) for a in (tiles, srow, sfirst))
+        self.n_tiles, self.n_split, self.n_split_tiles = (int(c) for c in counts)
+        self.tile_nnz, self.scratch = tile_nnz, None
+
+
 class CsrOperator:
     """One sparse operator  Y = diag(rs) . P(vals) . diag(cs) . X  over a CSR pattern P."""
 
-    def __init__(self, rowptr, col, n_rows, n_cols, vals=None, rs=None, cs=None, tile_nnz=0):
+    def __init__(self, rowptr, col, n_rows, n_cols, vals=None, rs=None, cs=None, tile_nnz=0, plan=None):
         self.rowptr, self.col = _i32(rowptr, "rowptr"), _i32(col, "col")
         self.vals, self.rs, self.cs = vals, rs, cs
         self.n_rows, self.n_cols = int(n_rows), int(n_cols)
         self.nnz = int(col.numel())
-        self._tiling = None
-        self._tiling_keep = None
-        if tile_nnz:
-            self.build_tiling(tile_nnz)
-
-    def build_tiling(self, tile_nnz: int):
-        """Split rows longer than tile_nnz into tiles (host-side, once per graph)."""
-        rp = self.rowptr.cpu().to(torch.int64)
-        deg = rp[1:] - rp[:-1]
-        if int(deg.max()) <= tile_nnz:
-            self._tiling = None
-            return
-        ntile = torch.clamp((deg + tile_nnz - 1) // tile_nnz, min=1)
-        split = torch.nonzero(ntile > 1).flatten()
-        whole = torch.nonzero(ntile <= 1).flatten()
-        rows, begs, first = [], [], [0]
-        for r in split.tolist():
-            k = int(ntile[r])
-            rows += [r] * k
-            begs += [int(rp[r]) + j * tile_nnz for j in range(k)]
-            first.append(first[-1] + k)
-        n_split_tiles = len(rows)
-        rows = torch.tensor(rows, dtype=torch.int64)
-        begs = torch.tensor(begs, dtype=torch.int64)
-        tile_row = torch.cat([rows, whole]).to(torch.int32)
-        tile_beg = torch.cat([begs, rp[whole]]).to(torch.int32)
-        dev = self.rowptr.device
-        keep = dict(tile_row=tile_row.to(dev), tile_beg=tile_beg.to(dev), split_row=split.to(torch.int32).to(dev),
-                    split_first=torch.tensor(first, dtype=torch.int32, device=dev), scratch=None,
-                    n_tiles=int(tile_row.numel()), tile_nnz=int(tile_nnz), n_split=int(split.numel()), n_split_tiles=n_split_tiles)
-        self._tiling_keep = keep
-        self._tiling = True
+        self.plan = plan if plan is not None else TilePlan(self.rowptr, self.n_rows, tile_nnz)
 
     def _tiling_struct(self, width):
-        if not self._tiling:
-            return None
-        k = self._tiling_keep
-        need = k["n_split_tiles"] * width
-        if k["scratch"] is None or k["scratch"].numel() < need:
-            k["scratch"] = torch.empty(need, dtype=torch.float32, device=self.rowptr.device)
-        return N.SpmmTiling(_p(k["tile_row"]), _p(k["tile_beg"]), _p(k["split_row"]), _p(k["split_first"]), _p(k["scratch"]),
-                            k["n_tiles"], k["tile_nnz"], k["n_split"], k["n_split_tiles"])
+        k = self.plan
+        need = k.n_split_tiles * width
+        if need and (k.scratch is None or k.scratch.numel() < need):
+            k.scratch = torch.empty(need, dtype=torch.float32, device=self.rowptr.device)
+        return N.SpmmTiling(_p(k.tiles), _p(k.split_row), _p(k.split_first), _p(k.scratch), k.n_tiles, k.n_split, k.n_split_tiles, 0)
 
     def apply(self, segs):
         """segs: list of (X, Y, Z_or_None, softmax: bool); all share d = X.shape[1]."""
@@ -107,12 +99,10 @@ class CsrOperator:
                 raise ValueError(f"spmm: shape mismatch X{tuple(X.shape)} Y{tuple(Y.shape)} for operator {self.n_rows}x{self.n_cols}")
             arr[i] = N.SpmmSeg(_p(X), _p(Y), _p(Z) if Z is not None else None, _ld(X), _ld(Y), _ld(Z) if Z is not None else 0,
                                N.SPMM_SOFTMAX if sm else 0, 0)
-        til = self._tiling_struct(d * min(len(segs), max(1, 1024 // d)))
+        til = self._tiling_struct(d * min(len(segs), N.MAX_SEG))
         N.check(N.lib().llmrec_spmm_csr_f32(_p(self.rowptr), _p(self.col), _p(self.vals), _p(self.rs), _p(self.cs),
-                                             self.n_rows, self.n_cols, d, arr, len(segs),
-                                             C.byref(til) if til is not None else None, _stream()), "spmm")
-        groups = -(-len(segs) // max(1, min(N.MAX_SEG, 1024 // d))) if d % 4 == 0 else -(-len(segs) // N.MAX_SEG)
-        _count(groups * (2 if (til is not None and til.n_split > 0) else 1))
+                                             self.n_rows, self.n_cols, d, arr, len(segs), C.byref(til), _stream()), "spmm")
+        _count(-(-len(segs) // N.MAX_SEG) * (2 if til.n_split > 0 else 1))
 
 
 def row_softmax(X, out=None):
@@ -176,7 +166,7 @@ def proj_wgrad_group(problems, d, mode=0):
     need = int(N.lib().llmrec_proj_wgrad_group_scratch(arr, len(problems), d, mode))
     scratch = _get_scratch(("wgrad", problems[0][0].device.index), need, problems[0][0].device) if need else None
     N.check(N.lib().llmrec_proj_wgrad_group_f32(arr, len(problems), d, mode, _p(scratch), need, _stream()), "proj_wgrad_group")
-    _count(3 + len(problems) if need else len(problems))
+    _count(4 if need else len(problems))
 
 
 def proj_wgrad(X, dY, dW, db, accumulate=False, mode=0):

@@ -81,7 +81,7 @@ def test_spmm_row_tiling_long_rows(d, nseg):
     m = _rand_csr(150, 4000, 30000, seed=5, power=True)       # a few rows with thousands of entries
     assert np.diff(m.indptr).max() > 1000
     op, dense = _op(m, cs=True, rs=True, tile=256)
-    assert op._tiling
+    assert op.plan.n_split > 0
     g = torch.Generator().manual_seed(4)
     X = [torch.randn(4000, d, generator=g).to(cuda) for _ in range(nseg)]
     Y = [torch.empty(150, d, device=cuda) for _ in range(nseg)]
