@@ -118,7 +118,6 @@ def run_ours(a):
         from llmrec_b200.dist_bench import run_sharded
         return run_sharded(a)
     from llmrec_b200 import main as M, ops
-    from llmrec_b200.engine import KernelTimer
     from llmrec_b200.runtime import set_args
     from llmrec_b200.utility import batch_test
     from llmrec_b200.utility.load_data import Data
@@ -127,7 +126,7 @@ def run_ours(a):
     ds, nu, ni, ne, dims, embed, wsize = WORKLOADS[a.workload]
     root = ensure_dataset(a.workload)
     args = set_args(parse_args(["--data_path", root, "--dataset", ds, "--debug", "--epoch", "1", "--embed_size", str(embed),
-                                "--weight_size", wsize, "--proj_mode", a.proj_mode, "--host_sampler", a.host_sampler]))
+                                "--weight_size", wsize, "--proj_mode", a.proj_mode, "--host_sampler", a.host_sampler, "--cuda_graph", str(a.graph)]))
     torch.cuda.set_device(0)
     M.set_seed(args.seed)
     gen = Data(path=resolve_dataset_dir(args.data_path, args.dataset), batch_size=args.batch_size, sampler=args.host_sampler)
@@ -144,21 +143,26 @@ def run_ours(a):
     for u, p, n in batches:
         t = torch.tensor([u, p, n], dtype=torch.int32, device="cuda")
         dev_batches.append((t[0], t[1], t[2]))
+    step = hp.train_step_graphed if a.graph else hp.train_step
     for i in range(W):
-        hp.train_step(*dev_batches[i])
+        step(*dev_batches[i])
     torch.cuda.synchronize()
     clocks = ClockSampler(0); clocks.start()
     l0 = ops.STATS["launches"]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(W, W + K):
-        hp.train_step(*dev_batches[i])
+        step(*dev_batches[i])
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     launches = ops.STATS["launches"] - l0
     n_inter = sum(len(b[0]) for b in batches[W:])
     value = n_inter / (ms / 1e3)
+    if a.graph:      # kernels per replayed step = launches of one eager step
+        l1 = ops.STATS["launches"]
+        snap = hp._snapshot_state(); hp.train_step(*dev_batches[0]); hp._restore_state(snap)
+        launches = (ops.STATS["launches"] - l1) * K
 
     # ---- end-to-end leg through Trainer's API ------------------------------------------------------------
     loss_host = torch.empty(K, dtype=torch.float32).pin_memory()
@@ -179,20 +183,35 @@ def run_ours(a):
     clk = clocks.finish()
     assert bool(torch.isfinite(loss_host).all()), "non-finite loss"
 
-    # ---- per-kernel-family timing (roofline leg) -------------------------------------------------------------
-    hp.timer = KernelTimer()
-    for i in range(K):
-        hp.train_step(*dev_batches[W + i])
+    # ---- per-kernel-family device time (roofline leg): each family's launches of one step, replayed R times from
+    #      its own CUDA graph between two events -> pure device time, no host gaps
+    u0, p0, n0 = dev_batches[0]
+    hp.forward(); hp.loss_and_output_grads(u0, p0, n0); hp.backward()
     torch.cuda.synchronize()
-    fam = {k: v[0] / K for k, v in hp.timer.totals().items()}     # ms per step
-    hp.timer = None
+    snap = hp._snapshot_state()
+    fams = {"proj_fwd": hp._proj_fwd, "spmm_fwd": hp._prop_fwd, "fuse_fwd": hp._fuse_fwd,
+            "loss_heads": lambda: hp.loss_and_output_grads(u0, p0, n0), "fuse_bwd": hp._fuse_bwd, "spmm_bwd": hp._chain_bwd,
+            "proj_wgrad": hp._wgrad, "adamw": lambda: hp.opt.step([hp.grads[k] for k in hp._opt_names])}
+    R = 10
+    fam = {}
+    for name, fn in fams.items():
+        fn(); torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(R):
+                fn()
+        g.replay(); torch.cuda.synchronize()
+        e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+        fam[name] = e0.elapsed_time(e1) / R
+    hp._restore_state(snap)
     bytes_ = step_bytes(tr)
     hbm, tf, src = peaks()
     top = max((k for k in fam if k in bytes_), key=lambda k: fam[k])
     ach = bytes_[top] / (fam[top] * 1e-3) / 1e9
     roof = {"kernel": top, "bound": "hbm", "achieved": round(ach, 1), "peak": hbm, "unit": "GB/s", "frac": round(ach / hbm, 4),
             "traffic": None, "peak_source": src, "alg_bytes_per_step": bytes_[top], "ms_per_step": round(fam[top], 4),
-            "families_ms": {k: round(v, 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1])}}
+            "families_ms": {k: round(v, 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1])},
+            "families_gbs": {k: round(bytes_[k] / (fam[k] * 1e-3) / 1e9, 1) for k in fam if k in bytes_}}
 
     # ---- eval leg ----------------------------------------------------------------------------------------------
     users = list(gen.test_set.keys())
@@ -210,7 +229,7 @@ def run_ours(a):
            "data": "synthetic", "impl": "ours",
            "config": {"workload": f"{a.workload}-shaped synthetic {nu}x{ni}, {gen.n_train} train edges, d={embed}, L={len(eval(wsize))}, batch=1024 (+aug edges), feature dims {list(dims)}",
                       "interactions_counted": "sum(len(users)) incl. augmented edges", "l2": "inputs larger than L2 (704 MB of features per step)",
-                      "proj_mode": a.proj_mode, "host_sampler": a.host_sampler},
+                      "proj_mode": a.proj_mode, "host_sampler": a.host_sampler, "cuda_graph": bool(a.graph)},
            "e2e": {"value": round(n_e2e / (ms_e2e / 1e3), 1), "unit": "interactions/s", "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": 4,
                    "ms_per_step": round(ms_e2e / K, 4)},
            "gpu_launches": launches, "clocks": clk, "roofline": roof, "eval": ev}
@@ -275,6 +294,7 @@ def main():
     ap.add_argument("--proj_mode", default="3xtf32")
     ap.add_argument("--host_sampler", default="python")
     ap.add_argument("--no-cpu", dest="no_cpu", action="store_true")
+    ap.add_argument("--graph", type=int, default=1)
     ap.add_argument("--cpu-steps", dest="cpu_steps", type=int, default=24)
     ap.add_argument("--cpu-eval-users", dest="cpu_eval_users", type=int, default=1500)
     a = ap.parse_args()

@@ -364,8 +364,7 @@ extern "C" int llmrec_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, co
     int rc = 0;
     if (p.total_f4 <= 8) rc = launch_spmm<8, 1, 4>(p, st);
     else if (p.total_f4 <= 16) rc = launch_spmm<16, 1, 4>(p, st);
-    else if (p.total_f4 <= 32) rc = launch_spmm<32, 1, 8>(p, st);
-    else rc = launch_spmm<32, 2, 4>(p, st);
+    else rc = launch_spmm<32, 1, 8>(p, st);  // wider concatenations: 32-chunk column windows over blockIdx.y
     if (rc) return rc;
   }
   return 0;

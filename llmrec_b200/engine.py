@@ -128,7 +128,13 @@ class HotPath:
 
     # ---- forward -------------------------------------------------------------------------------
     def forward(self):
-        d, L, S, m = self.d, self.L, self.S, self.cfg.proj_mode
+        self._proj_fwd()
+        self._prop_fwd()
+        self._fuse_fwd()
+        return self.U, self.I
+
+    def _proj_fwd(self):
+        d, m = self.d, self.cfg.proj_mode
         p, f = self.p, self.feats
         if self.has_feats:
             with self._t("proj_fwd"):                                                                                # Models.py:145-150
@@ -138,6 +144,9 @@ class HotPath:
                 probs.append((f["user"], p["user_trans.weight"], p["user_trans.bias"], self.P_usr))
                 probs.sort(key=lambda t: -t[0].shape[1])                       # long-K tiles first
                 ops.proj_fwd_group(probs, d, m)
+
+    def _prop_fwd(self):
+        L, S = self.L, self.S
         # step t even: ui (I_{t/2} -> U_{t/2+1});  t odd: iu (U_{(t+1)/2} -> I_{(t+1)/2}); softmax on the last layer
         n_steps = max(2 * L, 3 if self.has_feats else 0)
         for t in range(n_steps):
@@ -161,6 +170,8 @@ class HotPath:
                     segs.append((self.Ul[l], self.Il[l], None, l == L))                                                # :175,180
                 with self._t("spmm_fwd"):
                     self.iu.apply(segs)
+
+    def _fuse_fwd(self):
         c = self.cfg
         if self.has_feats:
             coefs = [c.model_cat_rate, c.model_cat_rate, c.user_cat_rate] + [c.item_cat_rate] * len(self.keys)
@@ -172,11 +183,16 @@ class HotPath:
             ops.fuse_fwd(self.Ul, su, coefs, self.U)                                                                   # :185-197
             ops.fuse_fwd(self.Il, si, coefs, self.I)
         self._fuse_args = (coefs, su, si)
-        return self.U, self.I
 
     # ---- backward: expects gU, gI and (GFu, GFi, Gprof_u, Gprof_i, GP_usr_direct) filled ---------------
     def backward(self, gp_usr_direct=None, gpi_direct=None):
-        d, L, S, m = self.d, self.L, self.S, self.cfg.proj_mode
+        self._fuse_bwd()
+        self._chain_bwd(gp_usr_direct, gpi_direct)
+        self._wgrad()
+        return self.grads
+
+    def _fuse_bwd(self):
+        L = self.L
         coefs, su, si = self._fuse_args
         if self.has_feats:
             dsu = [self.blk(self.GFu, 0), self.blk(self.GFu, 1), self.Gprof_u] + [self.blk(self.GFu, 2 + j) for j in range(len(self.keys))]
@@ -186,6 +202,9 @@ class HotPath:
         with self._t("fuse_bwd"):
             ops.fuse_bwd(self.gU, L + 1, self.dUl, su, coefs, dsu, True)
             ops.fuse_bwd(self.gI, L + 1, self.dIl, si, coefs, dsi, True)
+
+    def _chain_bwd(self, gp_usr_direct=None, gpi_direct=None):
+        L, S = self.L, self.S
         if self.has_feats:
             # prof_u = ui . prof_i  ->  Gprof_i += ui^T Gprof_u
             with self._t("spmm_bwd"):
@@ -217,6 +236,9 @@ class HotPath:
             with self._t("spmm_bwd"):
                 self.uiT.apply(segs)
             g_cur_I = dst
+
+    def _wgrad(self):
+        d, m = self.d, self.cfg.proj_mode
         if self.has_feats:
             f, g = self.feats, self.grads
             with self._t("proj_wgrad"):
@@ -225,7 +247,6 @@ class HotPath:
                 probs.append((f["text"], self.blk(self.GPi, 1), g["text_trans.weight"], g["text_trans.bias"], False))
                 probs.append((f["image"], self.blk(self.GPi, 0), g["image_trans.weight"], g["image_trans.bias"], False))
                 ops.proj_wgrad_group(probs, d, m)
-        return self.grads
 
     # ---- losses + their gradients w.r.t. the forward outputs ---------------------------------------------
     def loss_and_output_grads(self, users, pos, neg):
@@ -265,6 +286,53 @@ class HotPath:
         with self._t("adamw"):
             self.opt.step([self.grads[k] for k in self._opt_names])
         return self.loss
+
+    # ---- CUDA-graph replay of the whole step -----------------------------------------------------------
+    def train_step_graphed(self, users, pos, neg):
+        """Same as train_step, replayed from a CUDA graph captured per batch length B' (the ~45 launches
+        of a step cost more host time than device time at netflix scale).  users/pos/neg: int32 CUDA
+        tensors; they are copied into static index buffers the graph reads."""
+        B = int(users.numel())
+        if not hasattr(self, "_graphs"):
+            self._graphs, self._gidx = {}, None
+        if self._gidx is None or self._gidx.shape[1] < B:
+            self._gidx = torch.zeros((3, max(B, 2 * self.cfg.batch_size)), dtype=torch.int32, device=users.device)
+            self._graphs.clear()
+        self._gidx[0, :B].copy_(users, non_blocking=True)
+        self._gidx[1, :B].copy_(pos, non_blocking=True)
+        self._gidx[2, :B].copy_(neg, non_blocking=True)
+        g = self._graphs.get(B)
+        if g is None:
+            u, p, n = self._gidx[0, :B], self._gidx[1, :B], self._gidx[2, :B]
+            if not getattr(self, "_warm", False):
+                # one eager step sizes every lazily allocated scratch buffer; its parameter update is undone
+                snap = self._snapshot_state()
+                self.train_step(u, p, n)
+                self._restore_state(snap)
+                self._warm = True
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            snap = self._snapshot_state()
+            with torch.cuda.graph(g):
+                self.train_step(u, p, n)
+            self._restore_state(snap)        # capture does not execute, but keep state handling symmetric
+            self._graphs[B] = g
+        g.replay()
+        return self.loss
+
+    def _snapshot_state(self):
+        o = self.opt
+        return ([p.clone() for p in o.params], [m.clone() for m in o.m], [v.clone() for v in o.v], o.state.clone())
+
+    def _restore_state(self, snap):
+        o = self.opt
+        for dst, src in zip(o.params, snap[0]):
+            dst.copy_(src)
+        for dst, src in zip(o.m, snap[1]):
+            dst.copy_(src)
+        for dst, src in zip(o.v, snap[2]):
+            dst.copy_(src)
+        o.state.copy_(snap[3])
 
     def set_optimizer(self, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01):
         names = [k for k in PARAM_ORDER if k in self.p and (self.has_feats or k.endswith("embedding.weight"))]

@@ -101,6 +101,7 @@ class Trainer(object):
         # torch.optim.AdamW defaults: betas (0.9, 0.999), eps 1e-8, weight_decay 0.01 (main.py:100-104)
         self.optimizer = self.hot.set_optimizer(lr=self.lr)
         self._idx_host = None
+        self.use_graph = bool(getattr(args, "cuda_graph", 1))
         self._epoch_stats = torch.zeros(3, dtype=torch.float32, device=self.device)
 
     # ---- reference helper API (same names / returns) ----------------------------------------------
@@ -182,7 +183,7 @@ class Trainer(object):
 
     def train_batch(self, users, pos_items, neg_items):
         u, p, n = self.upload_batch(users, pos_items, neg_items)
-        loss = self.hot.train_step(u, p, n)
+        loss = self.hot.train_step_graphed(u, p, n) if self.use_graph else self.hot.train_step(u, p, n)
         # device-side epoch accumulators: [total, mf(main), emb(main)]
         self._epoch_stats[0:1] += loss
         self._epoch_stats[1:3] += self.hot.head_out[0:2]

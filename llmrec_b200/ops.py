@@ -46,7 +46,14 @@ def _i32(t, name="index"):
     return t
 
 
-DEFAULT_TILE_NNZ = int(os.environ.get("LLMREC_SPMM_TILE", "64"))
+DEFAULT_TILE_NNZ = int(os.environ.get("LLMREC_SPMM_TILE", "0"))      # 0 = size tiles from the graph
+
+
+def auto_tile_nnz(nnz):
+    """Tile size that yields ~8k tiles on small graphs (parallelism) and caps at 256 nnz on large ones
+    (amortised index reads, few long-row pieces)."""
+    t = nnz // 8192
+    return int(min(256, max(8, (t // 8) * 8)))
 
 
 class TilePlan:
@@ -54,8 +61,8 @@ class TilePlan:
     that use the same pattern (forward of one direction, backward of the other)."""
 
     def __init__(self, rowptr_dev, n_rows, tile_nnz=0, max_rows=15):
-        tile_nnz = int(tile_nnz) or DEFAULT_TILE_NNZ
         rp = np.ascontiguousarray(rowptr_dev.cpu().numpy().astype(np.int32))
+        tile_nnz = int(tile_nnz) or DEFAULT_TILE_NNZ or auto_tile_nnz(int(rp[-1]))
         lib = N.lib()
         counts = np.zeros(3, dtype=np.int32)
         N.check(lib.llmrec_spmm_plan_tiles(rp.ctypes.data, n_rows, tile_nnz, max_rows, None, None, None, counts.ctypes.data), "spmm_plan")

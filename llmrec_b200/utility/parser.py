@@ -58,6 +58,7 @@ _FLAGS = [
 # B200-side extras (not in the reference; all optional)
 _EXTRA = [
     ("proj_mode", dict(default="3xtf32", choices=["3xtf32", "tf32", "fp32"], help="tensor-core mode of the projection / scoring GEMMs")),
+    ("cuda_graph", dict(type=int, default=1, help="replay the training step from a CUDA graph (1) or launch eagerly (0)")),
     ("host_sampler", dict(default="python", choices=["native", "python"], help="bit-identical C sampler or the reference's Python loops")),
 ]
 

@@ -87,10 +87,11 @@ def test_fused_step_grads_match_reference(tiny_root, golden, mode):
         np.testing.assert_allclose(gten.cpu().numpy(), ref, rtol=2e-3, atol=1e-9 + 2e-5 * np.abs(ref).max(), err_msg=name)
 
 
-@pytest.mark.parametrize("mode", ["3xtf32", "fp32"])
-def test_epoch_matches_reference_golden(tiny_root, golden, mode):
-    """Same seed, same sampler stream, 8 steps of AdamW, then full-catalog eval: params, epoch loss, metrics, hit vectors."""
-    tr, gen, M = _trainer(tiny_root, ["--proj_mode", mode])
+@pytest.mark.parametrize("mode,graph", [("3xtf32", 1), ("fp32", 1), ("3xtf32", 0)])
+def test_epoch_matches_reference_golden(tiny_root, golden, mode, graph):
+    """Same seed, same sampler stream, 8 steps of AdamW, then full-catalog eval: params, epoch loss, metrics, hit vectors.
+    graph=1 replays the step from a CUDA graph (the default), graph=0 launches eagerly."""
+    tr, gen, M = _trainer(tiny_root, ["--proj_mode", mode, "--cuda_graph", str(graph)])
     M.set_seed(2022)
     logs = []
     tr.logger.logging = lambda s: logs.append(str(s))

@@ -42,7 +42,7 @@ if which in ("all", "spmm"):
     w = 1.0 / np.power(np.arange(ni) + 8.0, 0.8); w /= w.sum()
     rows = rng.integers(0, nu, 43000); cols = rng.choice(ni, size=43000, p=w)
     m = sp.csr_matrix((np.ones(43000, np.float32), (rows, cols)), shape=(nu, ni)); m.sum_duplicates(); m.data[:] = 1
-    for tile in (0, 32, 64):
+    for tile in (0, 8, 16, 32):
         g = BipartiteGraph(m, dev, tile_nnz=tile)
         for S in (8, 1):
             Xi = torch.randn(ni, S * d, device=dev); Yu = torch.empty(nu, S * d, device=dev); Yi = torch.empty(ni, S * d, device=dev)
