@@ -292,7 +292,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="netflix", choices=list(WORKLOADS))
     ap.add_argument("--proj_mode", default="3xtf32")
-    ap.add_argument("--host_sampler", default="python")
+    ap.add_argument("--host_sampler", default="native")
     ap.add_argument("--no-cpu", dest="no_cpu", action="store_true")
     ap.add_argument("--graph", type=int, default=1)
     ap.add_argument("--cpu-steps", dest="cpu_steps", type=int, default=24)

@@ -60,15 +60,16 @@ typedef struct {
 } llmrec_spmm_seg;
 
 typedef struct {
-  const int32_t* tiles;       /* [n_tiles][4] = {first row, #complete rows (0 = one piece of a long row), e0, e1};
-                                 pieces of long rows are numbered first (llmrec_spmm_plan_tiles builds this) */
+  const int32_t* tiles;       /* [n_tiles][8] = {first row, #complete rows (0 = one piece of a long row), e0, e1} followed by
+                                 16 one-byte row-end offsets relative to e0; 32-byte aligned; pieces of long rows are
+                                 numbered first (llmrec_spmm_plan_tiles builds this) */
   const int32_t* split_row;   /* [n_split] rows that were cut into pieces */
   const int32_t* split_first; /* [n_split+1] first piece (tile id) of each split row */
   float* scratch;             /* [n_split_tiles * min(nseg,16) * d] partial sums of the pieces */
   int32_t n_tiles, n_split, n_split_tiles, _pad;
 } llmrec_spmm_tiling;
 
-/* Host-side planner (runs once per graph): tiles of <= tile_nnz non-zeros, each a run of <= max_rows (<= 15)
+/* Host-side planner (runs once per graph): tiles of <= tile_nnz (8..248) non-zeros, each a run of <= max_rows (<= 15)
  * complete rows or one piece of a longer row.  Call with tiles_out == NULL to get the sizes in
  * counts_out = {n_tiles, n_split, n_split_tiles}, allocate, call again.  All pointers are HOST memory. */
 int llmrec_spmm_plan_tiles(const int32_t* rowptr_host, int32_t n_rows, int32_t tile_nnz, int32_t max_rows,
@@ -200,6 +201,13 @@ int64_t llmrec_score_topk_scratch(int32_t n_batch, int32_t n_items, int32_t d, i
 int llmrec_topk_hits(const int32_t* idx, int32_t n_batch, int32_t K, const int32_t* users,
                      const int32_t* truth_rowptr, const int32_t* truth_col, uint8_t* hits,
                      llmrec_stream_t stream);
+
+/* Host-side (CPU, no GPU needed) BPR item sampler, bit-identical to Data.sample()'s numpy draws
+ * (utility/load_data.py:166-187): hand over numpy's legacy MT19937 state (np.random.get_state()), get the
+ * positives / rejection-sampled negatives for `users` and the advanced state back.  All pointers HOST. */
+int llmrec_host_sample_items(uint32_t* mt_key /* [624] */, int32_t* mt_pos, const int32_t* users, int32_t n_users_in_batch,
+                             const int32_t* train_rowptr, const int32_t* train_col, int32_t n_items,
+                             int32_t* pos_out, int32_t* neg_out);
 
 /* small utilities used by the host mirror */
 int llmrec_fill_f32(float* p, int64_t n, float v, llmrec_stream_t stream);

@@ -16,8 +16,8 @@ struct BprParams {
   int n_heads; const int* users; const int* pos; const int* neg; int B; int n_keep; float c_emb; int d;
   float* out; float* loss; float* work; unsigned* counter;
 };
-// work layout per head h (stride WS = 6*B + 8): x[B], maxi[B], su[B], sp[B], sn[B], gcoef[B], eu, ep, en
-__device__ __forceinline__ float* work_of(const BprParams& p, int h) { return p.work + (size_t)h * (6 * (size_t)p.B + 8); }
+// work layout per head h (stride 7*B + 8): x[B], maxi[B], su[B], sp[B], sn[B], gcoef[B], keep[B], eu, ep, en
+__device__ __forceinline__ float* work_of(const BprParams& p, int h) { return p.work + (size_t)h * (7 * (size_t)p.B + 8); }
 
 __device__ __forceinline__ float logsigmoidf(float z) {  // min(z,0) - log1p(exp(-|z|))
   return fminf(z, 0.f) - log1pf(expf(-fabsf(z)));
@@ -60,32 +60,46 @@ __device__ float block_sum(float v, float* red) {
   return red[0];
 }
 
-// one CTA per head: exact ranks, kept-mean, regulariser, gradient coefficients
-__global__ void __launch_bounds__(1024) bpr_select_kernel(const BprParams p) {
-  extern __shared__ float sv[];  // B values
-  __shared__ float red[32];
-  __shared__ bool last;
-  const int h = blockIdx.x;
+// exact order statistics: rank_i = #{j : maxi_j < maxi_i or (== and j < i)}; 4 threads per element split the j range.
+// grid (ceil(B/64), heads) -- the O(B^2) compare work is spread over ~150 CTAs instead of one per head.
+__global__ void __launch_bounds__(256) bpr_rank_kernel(const BprParams p) {
+  extern __shared__ float sv[];  // B values of this head
+  const int h = blockIdx.y;
   float* w = work_of(p, h);
   const float* maxi = w + p.B;
   for (int i = threadIdx.x; i < p.B; i += blockDim.x) sv[i] = maxi[i];
   __syncthreads();
-  float kept_sum = 0.f, su = 0.f, sp = 0.f, sn = 0.f;
-  const float wmf = p.head[h].w_mf;
-  for (int i = threadIdx.x; i < p.B; i += blockDim.x) {
+  const int i = blockIdx.x * 64 + (threadIdx.x >> 2), part = threadIdx.x & 3;
+  int rank = 0;
+  if (i < p.B) {
     const float v = sv[i];
-    int rank = 0;
-    for (int j = 0; j < p.B; ++j) {
-      float o = sv[j];
+    for (int j = part; j < p.B; j += 4) {
+      const float o = sv[j];
       rank += (o < v) || (o == v && j < i);
     }
+  }
+  rank += __shfl_xor_sync(0xffffffffu, rank, 1);
+  rank += __shfl_xor_sync(0xffffffffu, rank, 2);
+  if (i < p.B && part == 0) {
     const bool keep = rank < p.n_keep;
-    if (keep) kept_sum += v;
     // d(-mean(maxi[keep]))/dx = -(1/n_keep) * sigmoid(-x); torch's log_sigmoid_backward form
-    float x = w[i];
-    float z = expf(-fabsf(x));
-    float dls = (x < 0.f) ? (1.f - z / (1.f + z)) : (z / (1.f + z));
-    w[5 * p.B + i] = keep ? (-wmf * dls / (float)p.n_keep) : 0.f;
+    const float x = w[i];
+    const float z = expf(-fabsf(x));
+    const float dls = (x < 0.f) ? (1.f - z / (1.f + z)) : (z / (1.f + z));
+    w[5 * p.B + i] = keep ? (-p.head[h].w_mf * dls / (float)p.n_keep) : 0.f;
+    w[6 * p.B + i] = keep ? 1.f : 0.f;
+  }
+}
+
+// one CTA per head: kept-mean (gcoef != 0 marks the kept set), regulariser sums, head outputs; last CTA adds the loss
+__global__ void __launch_bounds__(1024) bpr_select_kernel(const BprParams p) {
+  __shared__ float red[32];
+  __shared__ bool last;
+  const int h = blockIdx.x;
+  float* w = work_of(p, h);
+  float kept_sum = 0.f, su = 0.f, sp = 0.f, sn = 0.f;
+  for (int i = threadIdx.x; i < p.B; i += blockDim.x) {
+    if (w[6 * p.B + i] != 0.f) kept_sum += w[p.B + i];
     su += w[2 * p.B + i]; sp += w[3 * p.B + i]; sn += w[4 * p.B + i];
   }
   kept_sum = block_sum(kept_sum, red);
@@ -97,9 +111,9 @@ __global__ void __launch_bounds__(1024) bpr_select_kernel(const BprParams p) {
     p.out[h * 4 + 0] = mf; p.out[h * 4 + 1] = emb; p.out[h * 4 + 2] = (float)p.n_keep; p.out[h * 4 + 3] = 0.f;
     // d emb / d row = w_emb * c * (-4 row / (2S+eps)^2)
     const float we = p.head[h].w_emb * p.c_emb;
-    w[6 * p.B + 0] = -4.f * we / (du * du);
-    w[6 * p.B + 1] = -4.f * we / (dq * dq);
-    w[6 * p.B + 2] = -4.f * we / (dn * dn);
+    w[7 * p.B + 0] = -4.f * we / (du * du);
+    w[7 * p.B + 1] = -4.f * we / (dq * dq);
+    w[7 * p.B + 2] = -4.f * we / (dn * dn);
     __threadfence();
     unsigned done = atomicAdd(p.counter, 1u);
     last = (done == (unsigned)p.n_heads - 1);
@@ -125,7 +139,7 @@ __global__ void __launch_bounds__(256) bpr_grad_kernel(const BprParams p) {
   if (!hd.GU && !hd.GI) return;
   const float* w = work_of(p, h);
   const float g = w[5 * p.B + b];
-  const float eu = w[6 * p.B + 0], ep = w[6 * p.B + 1], en = w[6 * p.B + 2];
+  const float eu = w[7 * p.B + 0], ep = w[7 * p.B + 1], en = w[7 * p.B + 2];
   if (g == 0.f && hd.w_emb == 0.f) return;
   const int iu = p.users[b], ip = p.pos[b], in_ = p.neg[b];
   const float* u = hd.XU + (int64_t)iu * hd.ldxu;
@@ -167,7 +181,7 @@ __global__ void sqnorm_final_kernel(const float* partial, int nb, float c, float
 
 using namespace llmrec;
 
-extern "C" int64_t llmrec_bpr_work_elems(int32_t n_heads, int32_t B) { return (int64_t)n_heads * (6 * (int64_t)B + 8) + 4; }
+extern "C" int64_t llmrec_bpr_work_elems(int32_t n_heads, int32_t B) { return (int64_t)n_heads * (7 * (int64_t)B + 8) + 4; }
 
 extern "C" int llmrec_bpr_heads_f32(const llmrec_bpr_head* heads, int32_t n_heads,
                                     const int32_t* users, const int32_t* pos, const int32_t* neg, int32_t B,
@@ -181,15 +195,17 @@ extern "C" int llmrec_bpr_heads_f32(const llmrec_bpr_head* heads, int32_t n_head
   p.n_heads = n_heads; p.users = users; p.pos = pos; p.neg = neg; p.B = B; p.n_keep = n_keep; p.c_emb = regs0_over_bs; p.d = d;
   p.out = out; p.loss = loss_accum; p.work = work;
   // the last 4 floats of `work` hold the head counter (zeroed by the caller once; the kernel re-zeroes it)
-  p.counter = reinterpret_cast<unsigned*>(work + (size_t)n_heads * (6 * (size_t)B + 8));
+  p.counter = reinterpret_cast<unsigned*>(work + (size_t)n_heads * (7 * (size_t)B + 8));
   cudaStream_t st = as_stream(stream);
   dim3 grid((B + 7) / 8, n_heads);
   bpr_score_kernel<<<grid, 256, 0, st>>>(p);
   LLMREC_CHECK_LAUNCH("bpr_score");
   size_t smem = (size_t)B * sizeof(float);
   static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(bpr_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
-  bpr_select_kernel<<<n_heads, 1024, smem, st>>>(p);
+  if (!attr_set) { cudaFuncSetAttribute(bpr_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
+  bpr_rank_kernel<<<dim3((B + 63) / 64, n_heads), 256, smem, st>>>(p);
+  LLMREC_CHECK_LAUNCH("bpr_rank");
+  bpr_select_kernel<<<n_heads, 1024, 0, st>>>(p);
   LLMREC_CHECK_LAUNCH("bpr_select");
   bpr_grad_kernel<<<grid, 256, 0, st>>>(p);
   LLMREC_CHECK_LAUNCH("bpr_grad");

@@ -91,7 +91,7 @@ __device__ __forceinline__ void finish_row(const SpmmParams& p, const LaneChunks
 }
 
 template <int LPR, int CH, int U>
-__global__ void __launch_bounds__(256) spmm_tile_kernel(const SpmmParams p) {
+__global__ void __launch_bounds__(256, 4) spmm_tile_kernel(const SpmmParams p) {
   constexpr int RPW = 32 / LPR;  // tiles per warp
   const int lane = threadIdx.x & 31;
   const int lane_in = lane % LPR;
@@ -103,19 +103,16 @@ __global__ void __launch_bounds__(256) spmm_tile_kernel(const SpmmParams p) {
   LaneChunks<CH> lc;
   setup_chunks<LPR, CH>(p, blockIdx.y * (LPR * CH), lane_in, lc);
 
-  const int4 t = __ldg(p.tiles + tile);  // {first row, #complete rows (0 = piece of a long row), e0, e1}
+  // 32-byte tile descriptor: {first row, #complete rows (0 = piece of a long row), e0, e1} + 16 one-byte row-end
+  // deltas (rowptr[row0+i+1] - e0): no dependent rowptr read, the row boundaries travel with the descriptor.
+  const int4 t = __ldg(p.tiles + 2 * tile);
+  const uint4 dl = __ldg(reinterpret_cast<const uint4*>(p.tiles + 2 * tile + 1));
   const int row0 = t.x, nrows = t.y, e0 = t.z, e1 = t.w;
   const bool piece = nrows == 0;
-  // row pointers of the tile: entries 0..nrows live in two registers per lane (nrows <= 15 <= 2*LPR-1)
-  int rp_lo = 0x7fffffff, rp_hi = 0x7fffffff;
-  if (!piece) {
-    if (lane_in <= nrows) rp_lo = __ldg(p.rowptr + row0 + lane_in);
-    if (LPR < 16 && LPR + lane_in <= nrows) rp_hi = __ldg(p.rowptr + row0 + LPR + lane_in);
-  }
   auto row_end_of = [&](int i) -> int {  // end offset of local row i-1 == rowptr[row0 + i]
-    int lo = __shfl_sync(gmask, rp_lo, i & (LPR - 1), LPR);
-    int hi = __shfl_sync(gmask, rp_hi, i & (LPR - 1), LPR);
-    return (LPR < 16 && i >= LPR) ? hi : lo;
+    const int b = i - 1;
+    const unsigned wsel = (b >> 2) == 0 ? dl.x : ((b >> 2) == 1 ? dl.y : ((b >> 2) == 2 ? dl.z : dl.w));
+    return e0 + (int)((wsel >> ((b & 3) * 8)) & 0xffu);
   };
   int cur = 0;
   int row_end = piece ? e1 : row_end_of(1);
@@ -267,12 +264,12 @@ static int launch_spmm(const SpmmParams& p, cudaStream_t st) {
 
 using namespace llmrec;
 
-// Host-side tile planner (native graph-builder step).  Tiles are int32x4 {row0, nrows, e0, e1}; pieces of
+// Host-side tile planner (native graph-builder step).  Tiles are 8 x int32: {row0, nrows, e0, e1} + 16 row-end byte deltas; pieces of
 // long rows (nrows == 0) come first.  Call with tiles_out == NULL to size the outputs:
 // counts_out = {n_tiles, n_split, n_split_tiles}.
 extern "C" int llmrec_spmm_plan_tiles(const int32_t* rowptr_host, int32_t n_rows, int32_t tile_nnz, int32_t max_rows,
                                       int32_t* tiles_out, int32_t* split_row_out, int32_t* split_first_out, int32_t* counts_out) {
-  LLMREC_CHECK_ARG(tile_nnz >= 8 && max_rows >= 1 && max_rows <= 15, "spmm_plan: tile_nnz=%d max_rows=%d out of range", tile_nnz, max_rows);
+  LLMREC_CHECK_ARG(tile_nnz >= 8 && tile_nnz <= 248 && max_rows >= 1 && max_rows <= 15, "spmm_plan: tile_nnz=%d (8..248) max_rows=%d (1..15) out of range", tile_nnz, max_rows);
   int64_t n_split = 0, n_pieces = 0, n_groups = 0;
   // pass 1: pieces
   for (int32_t r = 0; r < n_rows; ++r) {
@@ -282,8 +279,9 @@ extern "C" int llmrec_spmm_plan_tiles(const int32_t* rowptr_host, int32_t n_rows
         split_row_out[n_split] = r;
         split_first_out[n_split] = (int32_t)n_pieces;
         for (int32_t b = rowptr_host[r]; b < rowptr_host[r + 1]; b += tile_nnz) {
-          int32_t* t = tiles_out + 4 * n_pieces++;
+          int32_t* t = tiles_out + 8 * n_pieces++;
           t[0] = r; t[1] = 0; t[2] = b; t[3] = b + tile_nnz < rowptr_host[r + 1] ? b + tile_nnz : rowptr_host[r + 1];
+          t[4] = t[5] = t[6] = t[7] = 0;
         }
       } else {
         n_pieces += (deg + tile_nnz - 1) / tile_nnz;
@@ -304,8 +302,10 @@ extern "C" int llmrec_spmm_plan_tiles(const int32_t* rowptr_host, int32_t n_rows
       ++r1;
     }
     if (tiles_out) {
-      int32_t* t = tiles_out + 4 * (n_pieces + n_groups);
+      int32_t* t = tiles_out + 8 * (n_pieces + n_groups);
       t[0] = r; t[1] = r1 - r; t[2] = rowptr_host[r]; t[3] = rowptr_host[r1];
+      uint8_t* dl = reinterpret_cast<uint8_t*>(t + 4);
+      for (int i = 0; i < 16; ++i) dl[i] = (uint8_t)(i < r1 - r ? rowptr_host[r + i + 1] - rowptr_host[r] : 0);
     }
     ++n_groups;
     r = r1;
@@ -364,7 +364,7 @@ extern "C" int llmrec_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, co
     int rc = 0;
     if (p.total_f4 <= 8) rc = launch_spmm<8, 1, 4>(p, st);
     else if (p.total_f4 <= 16) rc = launch_spmm<16, 1, 4>(p, st);
-    else rc = launch_spmm<32, 1, 8>(p, st);  // wider concatenations: 32-chunk column windows over blockIdx.y
+    else rc = launch_spmm<32, 1, 4>(p, st);  // wider concatenations: 32-chunk column windows over blockIdx.y
     if (rc) return rc;
   }
   return 0;

@@ -10,7 +10,8 @@ the CSR of its transpose and two fp32 scale vectors; the four operators the path
     ui^T = R^T diag(su)        rows=items   pattern CSR(R^T)  col scale su     (backward of ui)
     iu^T = R diag(si)          rows=users   pattern CSR(R)    col scale si     (backward of iu)
 
-HBM layout: rowptr int32[n+1], col int32[nnz] (no value array), scales fp32[n].
+HBM layout: rowptr int32[n+1], col int32[nnz], scales fp32[n]; forward operators carry no value array, the two
+transpose operators carry w[e] = scale[col[e]] (fp32[nnz]).
 """
 from __future__ import annotations
 
@@ -51,8 +52,12 @@ class BipartiteGraph:
         nu, ni = self.n_users, self.n_items
         self.ui = CsrOperator(self.rowptr_u, self.col_u, nu, ni, rs=self.su, tile_nnz=tile_nnz)
         self.iu = CsrOperator(self.rowptr_i, self.col_i, ni, nu, rs=self.si, tile_nnz=tile_nnz)
-        self.uiT = CsrOperator(self.rowptr_i, self.col_i, ni, nu, cs=self.su, plan=self.iu.plan)     # same pattern, same tiles
-        self.iuT = CsrOperator(self.rowptr_u, self.col_u, nu, ni, cs=self.si, plan=self.ui.plan)
+        # transposes: the column scale is gathered ONCE into a per-nnz weight array (coalesced with col in the kernel,
+        # no dependent cs[col] load); same pattern -> same tile plan as the forward operator of the other direction
+        self.w_uiT = self.su[self.col_i.long()].contiguous()
+        self.w_iuT = self.si[self.col_u.long()].contiguous()
+        self.uiT = CsrOperator(self.rowptr_i, self.col_i, ni, nu, vals=self.w_uiT, plan=self.iu.plan)
+        self.iuT = CsrOperator(self.rowptr_u, self.col_u, nu, ni, vals=self.w_iuT, plan=self.ui.plan)
         self.device = dev
 
     # the reference-facing COO tensors (what Trainer.ui_graph / iu_graph hold; main.py:128-134)

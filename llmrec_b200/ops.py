@@ -53,7 +53,7 @@ def auto_tile_nnz(nnz):
     """Tile size that yields ~8k tiles on small graphs (parallelism) and caps at 256 nnz on large ones
     (amortised index reads, few long-row pieces)."""
     t = nnz // 8192
-    return int(min(256, max(8, (t // 8) * 8)))
+    return int(min(248, max(8, (t // 8) * 8)))
 
 
 class TilePlan:
@@ -66,7 +66,7 @@ class TilePlan:
         lib = N.lib()
         counts = np.zeros(3, dtype=np.int32)
         N.check(lib.llmrec_spmm_plan_tiles(rp.ctypes.data, n_rows, tile_nnz, max_rows, None, None, None, counts.ctypes.data), "spmm_plan")
-        tiles = np.zeros((max(int(counts[0]), 1), 4), dtype=np.int32)
+        tiles = np.zeros((max(int(counts[0]), 1), 8), dtype=np.int32)
         srow = np.zeros(max(int(counts[1]), 1), dtype=np.int32)
         sfirst = np.zeros(int(counts[1]) + 1, dtype=np.int32)
         N.check(lib.llmrec_spmm_plan_tiles(rp.ctypes.data, n_rows, tile_nnz, max_rows, tiles.ctypes.data, srow.ctypes.data,
@@ -232,7 +232,7 @@ def bpr_heads(heads, users, pos, neg, n_keep, regs0_over_bs, out, loss, work):
     B = int(users.numel())
     N.check(N.lib().llmrec_bpr_heads_f32(arr, len(heads), _p(_i32(users)), _p(_i32(pos)), _p(_i32(neg)), B, int(n_keep),
                                           float(regs0_over_bs), d, _p(out), _p(loss), _p(work), _stream()), "bpr_heads")
-    _count(3)
+    _count(4)
 
 
 _partial = {}

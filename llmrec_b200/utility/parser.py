@@ -59,7 +59,7 @@ _FLAGS = [
 _EXTRA = [
     ("proj_mode", dict(default="3xtf32", choices=["3xtf32", "tf32", "fp32"], help="tensor-core mode of the projection / scoring GEMMs")),
     ("cuda_graph", dict(type=int, default=1, help="replay the training step from a CUDA graph (1) or launch eagerly (0)")),
-    ("host_sampler", dict(default="python", choices=["native", "python"], help="bit-identical C sampler or the reference's Python loops")),
+    ("host_sampler", dict(default="native", choices=["native", "python"], help="bit-identical C sampler or the reference's Python loops")),
 ]
 
 DATASET_ALIASES = {"netflix": "netflix_valid_item", "movielens": "preprocessed_raw_MovieLens", "movieLens": "preprocessed_raw_MovieLens"}
