@@ -56,7 +56,7 @@ class ClockSampler(threading.Thread):
 
     def run(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 self.rows.append([x.strip() for x in line.split(",")])
@@ -144,10 +144,10 @@ def run_ours(a):
         t = torch.tensor([u, p, n], dtype=torch.int32, device="cuda")
         dev_batches.append((t[0], t[1], t[2]))
     step = hp.train_step_graphed if a.graph else hp.train_step
+    clocks = ClockSampler(0); clocks.start()      # samples clocks / throttle reasons across the value and e2e legs
     for i in range(W):
         step(*dev_batches[i])
     torch.cuda.synchronize()
-    clocks = ClockSampler(0); clocks.start()
     l0 = ops.STATS["launches"]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

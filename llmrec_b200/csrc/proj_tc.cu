@@ -406,33 +406,45 @@ __global__ void __launch_bounds__(384, 1) proj_wgrad_tc_kernel(const __grid_cons
 }
 
 // dW[dc][f] = sum over (problems sharing this dW, in list order) x (row chunks, in order) of partial[item][f % 128][dc]
-// One launch for every output: block = (output feature tile, 32-feature quarter); fixed summation order -> deterministic.
+// One launch for every output.  Block = (output feature tile, group of 4 features): 64 float4 elements x 4 source
+// slices; each thread sums every 4th (problem, chunk) source with independent loads in flight, the 4 slices are
+// combined in a fixed order -> deterministic and latency-tolerant (the naive per-element loop was latency-bound).
 struct ReduceOut { float* dW; int k, n_src, accumulate, blk_start; int src[kMaxProb]; };
 struct ReduceParams { ReduceOut out[kMaxProb]; int n_out; int d; const float* partial; WgProblem prob[kMaxProb]; };
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const ReduceParams R) {
-  __shared__ float tile[32][257];  // [f][dc] padded
+  __shared__ float4 part[4][64];
   int o = 0;
   while (o + 1 < R.n_out && (int)blockIdx.x >= R.out[o + 1].blk_start) ++o;
   const ReduceOut ro = R.out[o];
+  const int d = R.d, f4_per_feat = d >> 2;                 // d % 32 == 0 on this path
+  const int feats_per_blk = 64 / f4_per_feat;              // 4 at d = 64, 2 at d = 128, 1 at d = 256
   const int local = blockIdx.x - ro.blk_start;
-  const int ft = local >> 2, q = local & 3, d = R.d;
-  for (int i = threadIdx.x; i < 32 * d; i += blockDim.x) {
-    const int f = i / d, dc = i - f * d;
-    float s = 0.f;
-    for (int j = 0; j < ro.n_src; ++j) {
-      const WgProblem pr = R.prob[ro.src[j]];
-      for (int c = 0; c < pr.chunks; ++c)
-        s += R.partial[((long long)(pr.item_start + c * pr.ft_tiles + ft) * BM + q * 32 + f) * d + dc];
+  const int groups_per_ft = BM / feats_per_blk;
+  const int ft = local / groups_per_ft, fg = local - ft * groups_per_ft;
+  const int e = threadIdx.x & 63, sl = threadIdx.x >> 6;
+  const int f = fg * feats_per_blk + e / f4_per_feat;      // feature inside the 128-feature tile
+  const int dc4 = e - (e / f4_per_feat) * f4_per_feat;     // float4 column
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  int idx = 0;
+  for (int j = 0; j < ro.n_src; ++j) {
+    const WgProblem pr = R.prob[ro.src[j]];
+#pragma unroll 4
+    for (int c = 0; c < pr.chunks; ++c, ++idx) {
+      if ((idx & 3) != sl) continue;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(R.partial + ((long long)(pr.item_start + c * pr.ft_tiles + ft) * BM + f) * d) + dc4);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
-    tile[f][dc] = s;
   }
+  part[sl][e] = s;
   __syncthreads();
-  for (int i = threadIdx.x; i < 32 * d; i += blockDim.x) {
-    const int dc = i >> 5, f = i & 31;
-    const int gf = ft * BM + q * 32 + f;
+  if (sl == 0) {
+    float4 a = part[0][e], b = part[1][e], c = part[2][e], g = part[3][e];
+    float4 t = make_float4((a.x + b.x) + (c.x + g.x), (a.y + b.y) + (c.y + g.y), (a.z + b.z) + (c.z + g.z), (a.w + b.w) + (c.w + g.w));
+    const int gf = ft * BM + f;
     if (gf < ro.k) {
-      float* p = ro.dW + (long long)dc * ro.k + gf;
-      *p = ro.accumulate ? (*p + tile[f][dc]) : tile[f][dc];
+      float* p = ro.dW + (long long)(dc4 * 4) * ro.k + gf;
+      if (ro.accumulate) { t.x += p[0]; t.y += p[ro.k]; t.z += p[2LL * ro.k]; t.w += p[3LL * ro.k]; }
+      p[0] = t.x; p[ro.k] = t.y; p[2LL * ro.k] = t.z; p[3LL * ro.k] = t.w;
     }
   }
 }
@@ -440,15 +452,17 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const ReduceParams R)
 // db[dc] (+)= sum_r dY[r][dc] : 16 row-slices per problem -> partial, then an ordered combine (deterministic;
 // problems sharing one db -- the 5 attribute matrices behind item_trans -- accumulate in problem order)
 struct ColsumParams { const float* dY[kMaxProb]; long long ld[kMaxProb]; long long n[kMaxProb]; float* db[kMaxProb]; int acc[kMaxProb]; int d; int n_prob; float* partial; };
-constexpr int kColsumSlices = 16;
+constexpr int kColsumSlices = 128;
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const ColsumParams P) {
   __shared__ float red[256];
   const int p = blockIdx.y, b = blockIdx.x, d = P.d;
   const int groups = 256 / d > 0 ? 256 / d : 1;  // d <= 256
   const int g = threadIdx.x / d, c = threadIdx.x - g * d;
   float s = 0.f;
-  if (g < groups && P.db[p])
-    for (long long r = (long long)b * groups + g; r < P.n[p]; r += (long long)kColsumSlices * groups) s += P.dY[p][r * P.ld[p] + c];
+  if (g < groups && P.db[p]) {
+#pragma unroll 4
+    for (long long r = (long long)b * groups + g; r < P.n[p]; r += (long long)kColsumSlices * groups) s += __ldg(P.dY[p] + r * P.ld[p] + c);
+  }
   red[threadIdx.x] = (g < groups) ? s : 0.f;
   __syncthreads();
   if (threadIdx.x < d) {
@@ -457,15 +471,26 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const ColsumParams 
     P.partial[((long long)p * kColsumSlices + b) * d + threadIdx.x] = t;
   }
 }
-__global__ void __launch_bounds__(256) colsum_final_kernel(const ColsumParams P) {
-  const int c = threadIdx.x;
-  if (c >= P.d) return;
+// one block per problem group is not possible (problems sharing db must be combined in order), so: one block, d columns x
+// (1024/d) slice-groups; each thread sums its slices for every problem, fixed-order combine, problems applied in order
+__global__ void __launch_bounds__(1024) colsum_final_kernel(const ColsumParams P) {
+  __shared__ float red[1024];
+  const int d = P.d, groups = 1024 / d;
+  const int g = threadIdx.x / d, c = threadIdx.x - g * d;
   for (int p = 0; p < P.n_prob; ++p) {
-    if (!P.db[p]) continue;
-    float t = 0.f;
-    for (int b = 0; b < kColsumSlices; ++b) t += P.partial[((long long)p * kColsumSlices + b) * P.d + c];
-    float* o = P.db[p] + c;
-    *o = P.acc[p] ? (*o + t) : t;
+    if (!P.db[p]) continue;   // uniform
+    float s = 0.f;
+    if (g < groups)
+      for (int b = g; b < kColsumSlices; b += groups) s += P.partial[((long long)p * kColsumSlices + b) * d + c];
+    red[threadIdx.x] = (g < groups) ? s : 0.f;
+    __syncthreads();
+    if (threadIdx.x < d) {
+      float t = 0.f;
+      for (int gg = 0; gg < groups; ++gg) t += red[gg * d + threadIdx.x];
+      float* o = P.db[p] + threadIdx.x;
+      *o = P.acc[p] ? (*o + t) : t;
+    }
+    __syncthreads();
   }
 }
 
@@ -592,12 +617,13 @@ int proj_wgrad_tc_group(const llmrec_proj_wgrad_problem* pr, int n_prob, int d, 
     LLMREC_CHECK_ARG(R.out[o].k == pr[p].k, "proj_wgrad: problems sharing dW must share k");
     R.out[o].src[R.out[o].n_src++] = p;
   }
-  for (int o = 0; o < R.n_out; ++o) { R.out[o].blk_start = blocks; blocks += ((R.out[o].k + BM - 1) / BM) * 4; }
+  const int feats_per_blk = 64 / (d / 4);
+  for (int o = 0; o < R.n_out; ++o) { R.out[o].blk_start = blocks; blocks += ((R.out[o].k + BM - 1) / BM) * (BM / feats_per_blk); }
   wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(R);
   LLMREC_CHECK_LAUNCH("wgrad_reduce");
   colsum_partial_kernel<<<dim3(kColsumSlices, n_prob), 256, 0, st>>>(C);
   LLMREC_CHECK_LAUNCH("colsum_partial");
-  colsum_final_kernel<<<1, 256, 0, st>>>(C);
+  colsum_final_kernel<<<1, 1024, 0, st>>>(C);
   LLMREC_CHECK_LAUNCH("colsum_final");
   return 0;
 }

@@ -50,10 +50,10 @@ DEFAULT_TILE_NNZ = int(os.environ.get("LLMREC_SPMM_TILE", "0"))      # 0 = size 
 
 
 def auto_tile_nnz(nnz):
-    """Tile size that yields ~8k tiles on small graphs (parallelism) and caps at 256 nnz on large ones
-    (amortised index reads, few long-row pieces)."""
-    t = nnz // 8192
-    return int(min(248, max(8, (t // 8) * 8)))
+    """32 non-zeros per tile on small graphs (parallelism without cutting ordinary rows into pieces), growing to 248
+    on large ones (amortised index reads, few long-row pieces)."""
+    t = nnz // 65536
+    return int(min(248, max(32, (t // 8) * 8)))
 
 
 class TilePlan:
