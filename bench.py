@@ -114,7 +114,7 @@ def run_ours(a):
     import torch
     import torch.distributed as dist
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
-    if world > 1:
+    if world > 1 or a.workload == "synthetic":
         from llmrec_b200.dist_bench import run_sharded
         return run_sharded(a)
     from llmrec_b200 import main as M, ops
@@ -290,7 +290,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="netflix", choices=list(WORKLOADS))
+    ap.add_argument("--workload", default="netflix", choices=list(WORKLOADS) + ["synthetic"])
+    ap.add_argument("--syn-scale", dest="syn_scale", type=float, default=1.0, help="size factor of the 10M x 1M x 200M synthetic graph")
     ap.add_argument("--proj_mode", default="3xtf32")
     ap.add_argument("--host_sampler", default="native")
     ap.add_argument("--no-cpu", dest="no_cpu", action="store_true")

@@ -209,6 +209,15 @@ int llmrec_host_sample_items(uint32_t* mt_key /* [624] */, int32_t* mt_pos, cons
                              const int32_t* train_rowptr, const int32_t* train_col, int32_t n_items,
                              int32_t* pos_out, int32_t* neg_out);
 
+/* Row helpers of the sharded (multi-GPU) path: epilogue of an item-side propagation applied AFTER the cross-rank
+ * sum of per-rank partials, and gather / scatter-add of batch rows by index (idx < 0 = row not owned: zeros / skipped). */
+int llmrec_row_scale_softmax_f32(const float* X, int64_t ldx, const float* scale, float* Y, int64_t ldy, int64_t n, int32_t d,
+                                 int32_t softmax, llmrec_stream_t stream);
+int llmrec_gather_rows_f32(const float* X, int64_t ldx, const int32_t* idx, int32_t n, int32_t d, float* out, int64_t ldo,
+                           llmrec_stream_t stream);
+int llmrec_scatter_add_rows_f32(const float* G, int64_t ldg, const int32_t* idx, int32_t n, int32_t d, float* Y, int64_t ldy,
+                                llmrec_stream_t stream);
+
 /* small utilities used by the host mirror */
 int llmrec_fill_f32(float* p, int64_t n, float v, llmrec_stream_t stream);
 

@@ -1,0 +1,74 @@
+// Small row-wise helpers of the sharded (multi-GPU) path:
+//   * Y = [softmax]( scale[r] * X[r,:] )  -- the epilogue of an item-side propagation AFTER the cross-rank sum of
+//     the per-rank partials (the single-GPU path fuses this into the SpMM store)
+//   * gather / scatter-add of embedding rows by index (batch rows exchanged between ranks)
+#include "common.cuh"
+
+namespace llmrec {
+__global__ void __launch_bounds__(256) row_scale_softmax_kernel(const float* __restrict__ X, int64_t ldx, const float* __restrict__ scale,
+                                                                float* __restrict__ Y, int64_t ldy, int64_t n, int d, int softmax) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (blockIdx.x * (int64_t)(blockDim.x >> 5)) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const float s = scale ? scale[row] : 1.0f;
+  const float* x = X + row * ldx;
+  float* y = Y + row * ldy;
+  if (!softmax) {
+    for (int j = lane; j < d; j += 32) y[j] = s * x[j];
+    return;
+  }
+  float m = -INFINITY;
+  for (int j = lane; j < d; j += 32) m = fmaxf(m, s * x[j]);
+  m = warp_max(m);
+  float t = 0.f;
+  for (int j = lane; j < d; j += 32) t += expf(s * x[j] - m);
+  t = warp_sum(t);
+  const float inv = 1.0f / t;
+  for (int j = lane; j < d; j += 32) y[j] = expf(s * x[j] - m) * inv;
+}
+// out[b,:] = idx[b] >= 0 ? X[idx[b],:] : 0
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ X, int64_t ldx, const int* __restrict__ idx, int n, int d,
+                                                          float* __restrict__ out, int64_t ldo) {
+  const int lane = threadIdx.x & 31;
+  const int b = (blockIdx.x * (blockDim.x >> 5)) + (threadIdx.x >> 5);
+  if (b >= n) return;
+  const int r = idx[b];
+  for (int j = lane; j < d; j += 32) out[(int64_t)b * ldo + j] = r >= 0 ? X[(int64_t)r * ldx + j] : 0.f;
+}
+// Y[idx[b],:] += G[b,:] for idx[b] >= 0 (duplicates allowed -> atomics)
+__global__ void __launch_bounds__(256) scatter_add_rows_kernel(const float* __restrict__ G, int64_t ldg, const int* __restrict__ idx, int n, int d,
+                                                               float* __restrict__ Y, int64_t ldy) {
+  const int lane = threadIdx.x & 31;
+  const int b = (blockIdx.x * (blockDim.x >> 5)) + (threadIdx.x >> 5);
+  if (b >= n) return;
+  const int r = idx[b];
+  if (r < 0) return;
+  for (int j = lane; j < d; j += 32) atomicAdd(Y + (int64_t)r * ldy + j, G[(int64_t)b * ldg + j]);
+}
+}  // namespace llmrec
+using namespace llmrec;
+
+extern "C" int llmrec_row_scale_softmax_f32(const float* X, int64_t ldx, const float* scale, float* Y, int64_t ldy, int64_t n, int32_t d,
+                                            int32_t softmax, llmrec_stream_t stream) {
+  LLMREC_REQUIRE_DEVICE();
+  if (n <= 0) return 0;
+  row_scale_softmax_kernel<<<(unsigned)((n + 7) / 8), 256, 0, as_stream(stream)>>>(X, ldx, scale, Y, ldy, n, d, softmax);
+  LLMREC_CHECK_LAUNCH("row_scale_softmax");
+  return 0;
+}
+extern "C" int llmrec_gather_rows_f32(const float* X, int64_t ldx, const int32_t* idx, int32_t n, int32_t d, float* out, int64_t ldo,
+                                      llmrec_stream_t stream) {
+  LLMREC_REQUIRE_DEVICE();
+  if (n <= 0) return 0;
+  gather_rows_kernel<<<(n + 7) / 8, 256, 0, as_stream(stream)>>>(X, ldx, idx, n, d, out, ldo);
+  LLMREC_CHECK_LAUNCH("gather_rows");
+  return 0;
+}
+extern "C" int llmrec_scatter_add_rows_f32(const float* G, int64_t ldg, const int32_t* idx, int32_t n, int32_t d, float* Y, int64_t ldy,
+                                           llmrec_stream_t stream) {
+  LLMREC_REQUIRE_DEVICE();
+  if (n <= 0) return 0;
+  scatter_add_rows_kernel<<<(n + 7) / 8, 256, 0, as_stream(stream)>>>(G, ldg, idx, n, d, Y, ldy);
+  LLMREC_CHECK_LAUNCH("scatter_add_rows");
+  return 0;
+}

@@ -1,0 +1,196 @@
+"""Multi-GPU (one process per GPU, NCCL over NVLink) form of the ID-propagation hot path  --  SURVEY.md 8e.
+
+Sharding.  Users are split into contiguous row ranges, one per rank; rank r keeps
+    R_r = R[users_r, :]  as CSR (local user rows x ALL item columns) and CSR(R_r^T) (all items x local users),
+    E_u[users_r], its AdamW moments and every user-sized activation;
+item-sized tensors ([ni x d]: E_i, I_l, gradients, AdamW moments) are REPLICATED and kept identical on every rank.
+Consequences (L layers; the reference has no multi-GPU code, the oracle is 1-GPU == G-GPU equality):
+    ui . X      = su (.) R_r X              local  (X = item-sized, replicated)                       no exchange
+    iu . Y      = si (.) sum_r R_r^T Y_r    every rank forms its [ni x d] partial, ONE all-reduce,    1 exchange / layer
+                                            then scale / softmax (llmrec_row_scale_softmax_f32)
+    ui^T . G    = sum_r R_r^T (su (.) G_r)  same exchange in the backward chain                       1 exchange / layer
+    iu^T . G    = R_r (si (.) G)            local
+    losses      the batch's user rows are summed into a [B' x d] buffer (owners fill, others zero, one tiny
+                all-reduce); every rank then evaluates the BPR/prune head redundantly on identical data -> identical
+                item gradients without an exchange, user-row gradients scattered to their owners.
+Only item-sized data ever crosses NVLink (4 all-reduces of ni*d*4 bytes per step at L = 2); user-sized data never moves.
+This is the ID-only configuration (no side-feature tables), the one the 10M x 1M synthetic benchmark uses.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .engine import HotPathConfig
+from .ops import CsrOperator
+
+
+def shard_bounds(n: int, world: int):
+    """Contiguous, balanced row ranges: rank r owns [b[r], b[r+1])."""
+    base, rem = divmod(n, world)
+    b = [0]
+    for r in range(world):
+        b.append(b[-1] + base + (1 if r < rem else 0))
+    return b
+
+
+def owner_local_index(users: torch.Tensor, lo: int, hi: int) -> torch.Tensor:
+    """int32 local row of each batch user on this rank, -1 where another rank owns it."""
+    u = users.to(torch.int64)
+    own = (u >= lo) & (u < hi)
+    return torch.where(own, u - lo, torch.full_like(u, -1)).to(torch.int32)
+
+
+def csr_from_sorted_rows(rows: torch.Tensor, n_rows: int) -> torch.Tensor:
+    counts = torch.bincount(rows, minlength=n_rows)
+    rp = torch.zeros(n_rows + 1, dtype=torch.int64, device=rows.device)
+    rp[1:] = torch.cumsum(counts, 0)
+    return rp.to(torch.int32)
+
+
+def build_shard_csr(u_local: torch.Tensor, items: torch.Tensor, nu_local: int, n_items: int, group=None):
+    """Device-agnostic part of the shard construction (also exercised on CPU with gloo in tests/test_dist_cpu.py):
+    CSR(R_r), CSR(R_r^T) and the (deg + 1e-8)^-1/2 scales; ITEM degrees are summed over ranks."""
+    key, _ = torch.sort(u_local.to(torch.int64) * n_items + items.to(torch.int64))
+    ul, it = key // n_items, key % n_items
+    rowptr_u = csr_from_sorted_rows(ul, nu_local)
+    col_u = it.to(torch.int32).contiguous()
+    keyt, _ = torch.sort(it * nu_local + ul)
+    rowptr_i = csr_from_sorted_rows(keyt // nu_local, n_items)
+    col_i = (keyt % nu_local).to(torch.int32).contiguous()
+    deg_u = (rowptr_u[1:] - rowptr_u[:-1]).to(torch.float64)
+    deg_i = (rowptr_i[1:] - rowptr_i[:-1]).to(torch.float64)
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(deg_i, group=group)                             # item degrees are global
+    inv = lambda d: torch.pow(d + 1e-8, -0.5).to(torch.float32)         # main.py:114-118 (never inf with the +1e-8)
+    return dict(rowptr_u=rowptr_u, col_u=col_u, rowptr_i=rowptr_i, col_i=col_i, su=inv(deg_u), si=inv(deg_i), nnz=int(key.numel()))
+
+
+class ShardedGraph:
+    """Local shard of the bipartite graph.  u_local/items: int64 edge lists (local user row, global item), unique pairs."""
+
+    def __init__(self, u_local: torch.Tensor, items: torch.Tensor, nu_local: int, n_items: int, group=None, tile_nnz: int = 0):
+        c = build_shard_csr(u_local, items, nu_local, n_items, group)
+        self.nu_local, self.n_items, self.nnz = int(nu_local), int(n_items), c["nnz"]
+        self.su, self.si = c["su"], c["si"]
+        rowptr_u, col_u, rowptr_i, col_i = c["rowptr_u"], c["col_u"], c["rowptr_i"], c["col_i"]
+        self.rowptr_u, self.col_u, self.rowptr_i, self.col_i = rowptr_u, col_u, rowptr_i, col_i
+        # ui: rows = local users (row scale su).  iu_raw / uiT_raw: rows = items, partial sums to be all-reduced.
+        self.ui = CsrOperator(rowptr_u, col_u, nu_local, n_items, rs=self.su, tile_nnz=tile_nnz)
+        self.iu_raw = CsrOperator(rowptr_i, col_i, n_items, nu_local, tile_nnz=tile_nnz)
+        self.uiT_raw = CsrOperator(rowptr_i, col_i, n_items, nu_local, vals=self.su[col_i.long()].contiguous(), plan=self.iu_raw.plan)
+        self.iuT = CsrOperator(rowptr_u, col_u, nu_local, n_items, vals=self.si[col_u.long()].contiguous(), plan=self.ui.plan)
+
+
+class ShardedHotPath:
+    """ID-only training step over a ShardedGraph; world size 1 reproduces engine.HotPath(feats=None) exactly."""
+
+    def __init__(self, graph: ShardedGraph, E_u_local: torch.Tensor, E_i: torch.Tensor, cfg: HotPathConfig, user_lo: int, group=None):
+        self.g, self.cfg, self.group = graph, cfg, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.E_u, self.E_i = E_u_local, E_i
+        self.lo, self.hi = int(user_lo), int(user_lo) + E_u_local.shape[0]
+        nu, ni, d, L = E_u_local.shape[0], E_i.shape[0], cfg.embed_size, cfg.n_layers
+        self.nu, self.ni, self.d, self.L = nu, ni, d, L
+        dev = E_i.device
+        new = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+        self.Ul = [E_u_local] + [new(nu, d) for _ in range(L)]
+        self.Il = [E_i] + [new(ni, d) for _ in range(L)]
+        self.U, self.I = new(nu, d), new(ni, d)
+        self.part = new(ni, d)                       # per-rank partial of an item-side product (all-reduced in place)
+        self.gU, self.gI = new(nu, d), new(ni, d)
+        self.g_Eu, self.g_Ei = new(nu, d), new(ni, d)
+        self.dIl, self.bufU, self.bufI, self.tmpI = new(ni, d), new(nu, d), new(ni, d), new(ni, d)
+        self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.head_out = torch.zeros(4, dtype=torch.float32, device=dev)
+        self._B = None
+        self.opt = ops.AdamW([E_u_local, E_i], lr=1e-4)
+        self.comm_bytes = 0
+
+    def set_lr(self, lr):
+        self.opt.lr = lr
+
+    def _allreduce(self, t):
+        if self.world > 1:
+            dist.all_reduce(t, group=self.group)
+            self.comm_bytes += t.numel() * 4
+
+    # -- forward (Models.py:169-186) ------------------------------------------------------------------------
+    def forward(self):
+        L = self.L
+        for l in range(1, L + 1):
+            self.g.ui.apply([(self.Il[l - 1], self.Ul[l], None, l == L)])                    # U_l = [softmax] ui . I_{l-1}
+            self.g.iu_raw.apply([(self.Ul[l], self.part, None, False)])                       # partial of R^T U_l
+            self._allreduce(self.part)
+            ops.row_scale_softmax(self.part, self.g.si, self.Il[l], l == L)                   # I_l = [softmax] si (.) sum
+        ops.fuse_fwd(self.Ul, [], [], self.U)                                                 # mean over layers (:185-186)
+        ops.fuse_fwd(self.Il, [], [], self.I)
+        return self.U, self.I
+
+    # -- loss + output grads ------------------------------------------------------------------------------------
+    def loss_and_output_grads(self, users, pos, neg):
+        """users: GLOBAL user ids (int32, identical on every rank); pos/neg: item ids."""
+        c = self.cfg
+        B = int(users.numel())
+        if self._B != B:
+            dev = users.device
+            self._B = B
+            self.Ub, self.gUb = torch.empty(B, self.d, device=dev), torch.empty(B, self.d, device=dev)
+            self.arange = torch.arange(B, dtype=torch.int32, device=dev)
+            self.work = ops.bpr_work(1, B, dev)
+        local = owner_local_index(users, self.lo, self.hi)
+        ops.gather_rows(self.U, local, self.Ub)                                               # owners fill, others zero
+        self._allreduce(self.Ub)
+        self.loss.zero_(); self.gUb.zero_(); self.gI.zero_(); self.gU.zero_()
+        n_keep = int((1 - c.prune_loss_drop_rate) * B)
+        ops.bpr_heads([(self.Ub, self.I, self.gUb, self.gI, 1.0, 1.0)], self.arange, pos, neg, n_keep, c.regs0 / c.batch_size,
+                      self.head_out, self.loss, self.work)
+        ops.scatter_add_rows(self.gUb, local, self.gU)
+        return self.loss
+
+    # -- backward chain ---------------------------------------------------------------------------------------------
+    def backward(self):
+        L = self.L
+        ops.fuse_bwd(self.gU, L + 1, self.g_Eu, [], [], [], True)                             # dUl (= grad of E_u) = gU/(L+1)
+        ops.fuse_bwd(self.gI, L + 1, self.dIl, [], [], [], True)
+        g_cur = self.dIl
+        for l in range(L, 0, -1):
+            src = ops.row_softmax_bwd(self.Il[l], g_cur, out=self.tmpI) if l == L else g_cur
+            self.g.iuT.apply([(src, self.bufU, self.g_Eu, False)])                            # gU_l = dUl + iu^T src   (local rows)
+            if l == L:
+                ops.row_softmax_bwd(self.Ul[l], self.bufU, out=self.bufU)
+            self.g.uiT_raw.apply([(self.bufU, self.part, None, False)])                       # partial of ui^T gU_l
+            self._allreduce(self.part)
+            dst = self.g_Ei if l == 1 else self.bufI
+            torch.add(self.part, self.dIl, out=dst)                                           # gI_{l-1} = dIl + sum
+            g_cur = dst
+        return self.g_Eu, self.g_Ei
+
+    def train_step(self, users, pos, neg):
+        self.forward()
+        self.loss_and_output_grads(users, pos, neg)
+        self.backward()
+        self.opt.step([self.g_Eu, self.g_Ei])
+        return self.loss
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# synthetic graphs of the large configuration, generated on the device shard by shard
+# --------------------------------------------------------------------------------------------------------------------
+def synthetic_shard(n_users, n_items, n_edges, rank, world, device, seed=0, zipf_a=0.8):
+    """Edges of this rank's users: every user >= 1 edge, item popularity ~ (rank + 16)^-a; duplicates removed.
+    Deterministic in (seed, user range) only up to the per-rank generator, i.e. each rank's shard is reproducible."""
+    b = shard_bounds(n_users, world)
+    lo, hi = b[rank], b[rank + 1]
+    nu = hi - lo
+    g = torch.Generator(device=device).manual_seed(seed * 1000003 + rank)
+    extra = int(round(n_edges * nu / n_users)) - nu
+    w = torch.pow(torch.arange(n_items, device=device, dtype=torch.float64) + 16.0, -zipf_a)
+    cdf = torch.cumsum(w / w.sum(), 0).to(torch.float32)
+    perm = torch.randperm(n_items, device=device, generator=g)
+    users = torch.cat([torch.arange(nu, device=device), torch.randint(0, nu, (max(extra, 0),), device=device, generator=g)])
+    items = perm[torch.searchsorted(cdf, torch.rand(users.numel(), device=device, generator=g)).clamp_(max=n_items - 1)]
+    key = torch.unique(users * n_items + items)
+    return key // n_items, key % n_items, lo, hi

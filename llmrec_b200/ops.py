@@ -300,5 +300,23 @@ def topk_hits(idx, users, truth_rowptr, truth_col):
     return hits
 
 
+def row_scale_softmax(X, scale, out, softmax):
+    N.check(N.lib().llmrec_row_scale_softmax_f32(_p(_mat(X)), _ld(X), _p(scale), _p(_mat(out)), _ld(out), X.shape[0], X.shape[1],
+                                                  1 if softmax else 0, _stream()), "row_scale_softmax")
+    _count()
+    return out
+
+
+def gather_rows(X, idx, out):
+    N.check(N.lib().llmrec_gather_rows_f32(_p(_mat(X)), _ld(X), _p(_i32(idx)), idx.numel(), X.shape[1], _p(_mat(out)), _ld(out), _stream()), "gather_rows")
+    _count()
+    return out
+
+
+def scatter_add_rows(G, idx, Y):
+    N.check(N.lib().llmrec_scatter_add_rows_f32(_p(_mat(G)), _ld(G), _p(_i32(idx)), idx.numel(), G.shape[1], _p(_mat(Y)), _ld(Y), _stream()), "scatter_add_rows")
+    _count()
+
+
 def fill(t, v):
     N.check(N.lib().llmrec_fill_f32(_p(t), t.numel(), float(v), _stream()), "fill")
