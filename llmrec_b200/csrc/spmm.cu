@@ -18,6 +18,7 @@
 //   * neighbour rows come in with 128-bit read-only loads, U x CH in flight per lane; row scale,
 //     optional row-softmax over a segment's d columns (lane-group shuffle reduction), optional addend
 //     and the store are fused at the row boundary.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace llmrec {
@@ -90,8 +91,8 @@ __device__ __forceinline__ void finish_row(const SpmmParams& p, const LaneChunks
   }
 }
 
-template <int LPR, int CH, int U>
-__global__ void __launch_bounds__(256, 4) spmm_tile_kernel(const SpmmParams p) {
+template <int LPR, int CH, int U, int MINB = 4>
+__global__ void __launch_bounds__(256, MINB) spmm_tile_kernel(const SpmmParams p) {
   constexpr int RPW = 32 / LPR;  // tiles per warp
   const int lane = threadIdx.x & 31;
   const int lane_in = lane % LPR;
@@ -244,13 +245,13 @@ __global__ void spmm_scalar_kernel(const SpmmParams p) {
   }
 }
 
-template <int LPR, int CH, int U>
+template <int LPR, int CH, int U, int MINB = 4>
 static int launch_spmm(const SpmmParams& p, cudaStream_t st) {
   constexpr int RPW = 32 / LPR;
   const int warps = (p.n_tiles + RPW - 1) / RPW;
   const int blocks = (warps + 7) / 8;
   const int windows = (p.total_f4 + LPR * CH - 1) / (LPR * CH);
-  if (blocks > 0) spmm_tile_kernel<LPR, CH, U><<<dim3(blocks, windows), 256, 0, st>>>(p);
+  if (blocks > 0) spmm_tile_kernel<LPR, CH, U, MINB><<<dim3(blocks, windows), 256, 0, st>>>(p);
   LLMREC_CHECK_LAUNCH("spmm_tile");
   if (p.n_split > 0) {
     const int fw = (p.total_f4 + 32 * CH - 1) / (32 * CH);
@@ -364,7 +365,16 @@ extern "C" int llmrec_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, co
     int rc = 0;
     if (p.total_f4 <= 8) rc = launch_spmm<8, 1, 4>(p, st);
     else if (p.total_f4 <= 16) rc = launch_spmm<16, 1, 4>(p, st);
-    else rc = launch_spmm<32, 1, 4>(p, st);  // wider concatenations: 32-chunk column windows over blockIdx.y
+    else {  // 32 lanes x one 16-byte chunk; wider concatenations run as 32-chunk column windows over blockIdx.y
+      static const int variant = getenv("LLMREC_SPMM_VARIANT") ? atoi(getenv("LLMREC_SPMM_VARIANT")) : 0;
+      switch (variant) {
+        case 1: rc = launch_spmm<32, 1, 8, 3>(p, st); break;   // 8 gathers in flight per lane, 24 warps/SM
+        case 2: rc = launch_spmm<32, 1, 8, 4>(p, st); break;
+        case 3: rc = launch_spmm<32, 1, 4, 6>(p, st); break;   // 48 warps/SM
+        case 4: rc = launch_spmm<32, 1, 2, 8>(p, st); break;   // 64 warps/SM
+        default: rc = launch_spmm<32, 1, 4, 4>(p, st); break;
+      }
+    }
     if (rc) return rc;
   }
   return 0;

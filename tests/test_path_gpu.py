@@ -159,3 +159,48 @@ def test_no_feature_mode_and_layers(tiny_root):
         assert abs(float(hp.loss) - float(mf + emb)) < 1e-5
         torch.testing.assert_close(grads["user_id_embedding.weight"].cpu(), eu.grad, rtol=1e-3, atol=1e-8)
         torch.testing.assert_close(grads["item_id_embedding.weight"].cpu(), ei.grad, rtol=1e-3, atol=1e-8)
+
+
+def test_movielens_config_d128_L3_vs_oracle(tmp_path):
+    """BASELINE.json configs[2]: movielens keys, d=128, 3 ID layers, image/text/attribute projections + fusion:
+    forward, loss and one fused AdamW step against the CPU oracle on the same seeded inputs."""
+    from llmrec_b200 import main as M
+    from llmrec_b200.runtime import set_args
+    from llmrec_b200.synth import make_dataset
+    from llmrec_b200.utility import batch_test
+    from llmrec_b200.utility.load_data import Data
+    from llmrec_b200.utility.parser import parse_args, resolve_dataset_dir
+    from oracle import llmrec_oracle as O
+    root = str(tmp_path) + "/"
+    make_dataset(root, dataset="movielens", n_users=260, n_items=330, n_inter=1300, dims=(64, 96, 128), seed=3)
+    args = set_args(parse_args(["--data_path", root, "--dataset", "movielens", "--batch_size", "128", "--debug", "--embed_size", "128",
+                                "--weight_size", "[128,128,128]", "--lr", "0.001"]))
+    ddir = resolve_dataset_dir(args.data_path, args.dataset)
+    M.set_seed(11)
+    gen = Data(path=ddir, batch_size=128)
+    batch_test.init(gen, args)
+    tr = M.Trainer(data_config={}, data_generator=gen)
+    torch.set_num_threads(2)
+    data = O.load_dataset(ddir)
+    O.set_seed(11)
+    cfg = O.OracleConfig(embed_size=128, weight_size=(128, 128, 128), batch_size=128, lr=1e-3)
+    otr = O.OracleTrainer(data, cfg)
+    for k in O.PARAM_NAMES:
+        np.testing.assert_array_equal(tr.model_mm.state_dict()[k].cpu().numpy(), otr.params[k].detach().numpy())
+    U, I = tr.hot.forward()
+    with torch.no_grad():
+        out = otr.forward()
+    np.testing.assert_allclose(U.cpu().numpy(), out["U"].numpy(), rtol=3e-5, atol=3e-6)
+    np.testing.assert_allclose(I.cpu().numpy(), out["I"].numpy(), rtol=3e-5, atol=3e-6)
+    M.set_seed(5)
+    users, pos, neg = tr.sample_batch()
+    loss = float(tr.train_batch(users, pos, neg))
+    oloss, _ = otr.step(users, pos, neg)
+    assert abs(loss - oloss) < 3e-5 * max(1.0, abs(oloss)), (loss, oloss)
+    sd = tr.model_mm.state_dict()
+    for k in O.PARAM_NAMES:
+        np.testing.assert_allclose(sd[k].cpu().numpy(), otr.params[k].detach().numpy(), rtol=5e-3, atol=2e-5, err_msg=k)
+    res = tr.test(list(gen.test_set.keys()), is_val=False)
+    ores, _ = otr.test()
+    for k in ("recall", "ndcg", "precision", "hit_ratio"):
+        np.testing.assert_allclose(res[k], ores[k], atol=1e-4)
