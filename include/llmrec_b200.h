@@ -186,9 +186,12 @@ int llmrec_adamw_step_f32(float* const* p_host, const float* const* g_host, floa
  * Full-catalog scoring + top-K (utility/batch_test.py:149-152 scores, :21-36,100-102 ranking).
  *   score[b,i] = <U[users[b]], I[i]>;  train items of the user are excluded; top-K by score,
  *   ties -> lowest item id (heapq.nlargest over ascending candidates).
- * mask CSR: mask_rowptr[int64? no: int32][n_users_total+1], mask_col sorted or not.  users = int32[b].
- * out_idx int32 [b x K], out_val fp32 [b x K] (may be NULL).  K <= 64.
- * mode: 0 = tcgen05 3xTF32 + fused select, 2 = exact fp32 SIMT.
+ * mask CSR: mask_rowptr int32[n_users_total+1], mask_col int32 with every row SORTED ASCENDING (the fused
+ * selection walks it with a merge pointer).  users = int32[b].
+ * out_idx int32 [b x K], out_val fp32 [b x K] (may be NULL; exact fp32 scores).  K <= 64.
+ * mode: 0 = tcgen05 3xTF32 scoring with the select fused into the epilogue + exact fp32 rescoring of the
+ *           K+16.. candidates (d in {32,64,96,128}); 2 = exact fp32 SIMT.  Both return the same lists unless two
+ *           scores closer than the TF32x3 rounding (~1e-5 relative) straddle rank K+16.
  * --------------------------------------------------------------------------------------------- */
 int llmrec_score_topk_f32(const float* U, int64_t ldu, const float* I, int64_t ldi,
                           const int32_t* users, int32_t n_batch, int32_t n_items, int32_t d,

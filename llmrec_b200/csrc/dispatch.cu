@@ -10,6 +10,9 @@ bool proj_tc_supported(int d, int64_t ldx, const void* X, int k, bool wgrad);
 int proj_fwd_tc_group(const llmrec_proj_fwd_problem*, int, int, int, cudaStream_t);
 int proj_wgrad_tc_group(const llmrec_proj_wgrad_problem*, int, int, int, float*, int64_t, cudaStream_t);
 int64_t proj_wgrad_tc_scratch(const llmrec_proj_wgrad_problem*, int, int);
+bool score_tc_supported(int d, int K, long long ldu, long long ldi, const void* U, const void* I);
+long long score_tc_scratch(int n_batch, int n_items, int d, int K);
+int score_topk_tc(const float*, long long, const float*, long long, const int*, int, int, int, const int*, const int*, int, int*, float*, float*, long long, cudaStream_t);
 }  // namespace llmrec
 using namespace llmrec;
 
@@ -95,9 +98,9 @@ extern "C" int llmrec_proj_wgrad_f32(const float* X, int64_t ldx, const float* d
 }
 
 extern "C" int64_t llmrec_score_topk_scratch(int32_t n_batch, int32_t n_items, int32_t d, int32_t K, int32_t mode) {
-  (void)d; (void)K; (void)mode;
+  if (mode != 2 && (d == 32 || d == 64 || d == 96 || d == 128) && K <= 64) return score_tc_scratch(n_batch, n_items, d, K);
   int64_t want = (int64_t)n_batch * n_items;
-  int64_t cap = (int64_t)1 << 28;  // 1 GiB of fp32 scores at most; the kernel loops over user sub-blocks
+  int64_t cap = (int64_t)1 << 28;  // 1 GiB of fp32 scores at most; the SIMT kernel loops over user sub-blocks
   if (want > cap) want = (cap / n_items) * n_items;
   if (want < n_items) want = n_items;
   return want;
@@ -109,6 +112,7 @@ extern "C" int llmrec_score_topk_f32(const float* U, int64_t ldu, const float* I
   LLMREC_REQUIRE_DEVICE();
   LLMREC_CHECK_ARG(K >= 1 && K <= 64 && K <= n_items, "score_topk: K=%d unsupported (1..64, <= n_items)", K);
   if (n_batch <= 0) return 0;
-  (void)mode;
+  if (mode != 2 && score_tc_supported(d, K, ldu, ldi, U, I))
+    return score_topk_tc(U, ldu, I, ldi, users, n_batch, n_items, d, mask_rowptr, mask_col, K, out_idx, out_val, scratch, scratch_elems, as_stream(stream));
   return score_topk_simt(U, ldu, I, ldi, users, n_batch, n_items, d, mask_rowptr, mask_col, K, out_idx, out_val, scratch, scratch_elems, as_stream(stream));
 }

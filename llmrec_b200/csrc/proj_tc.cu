@@ -91,12 +91,6 @@ struct FwdParams {
   int n_prob, total_tiles, d, stages, tmem_cols;
 };
 
-struct PipeState {
-  int stage = 0; uint32_t phase = 0; int nstages;
-  __device__ explicit PipeState(int n) : nstages(n) {}
-  __device__ void advance() { if (++stage == nstages) { stage = 0; phase ^= 1; } }
-};
-
 template <bool SPLIT>
 __global__ void __launch_bounds__(384, 1) proj_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
   extern __shared__ uint8_t smem_raw[];

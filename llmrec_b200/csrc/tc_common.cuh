@@ -137,6 +137,13 @@ __device__ __forceinline__ void split_tile_inplace(float4* tile, float4* lo, int
   }
 }
 
+// ring-buffer cursor shared by the producer / consumer roles of a pipeline
+struct PipeState {
+  int stage = 0; uint32_t phase = 0; int nstages;
+  __device__ explicit PipeState(int n) : nstages(n) {}
+  __device__ void advance() { if (++stage == nstages) { stage = 0; phase ^= 1; } }
+};
+
 }  // namespace tc
 
 // ---- host side: tensor-map encoding through the driver entry point (no -lcuda link dependency) ----

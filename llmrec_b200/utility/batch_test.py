@@ -33,7 +33,7 @@ def init(generator, args=None):
 def _device_csr(which, device):
     key = (which, str(device))
     if key not in _dev_cache:
-        rp, col = data_generator.csr(which)
+        rp, col = data_generator.csr(which, sorted_rows=True)
         _dev_cache[key] = (torch.from_numpy(rp).to(device), torch.from_numpy(col).to(device))
     return _dev_cache[key]
 
@@ -59,6 +59,8 @@ def test_torch(ua_embeddings, ia_embeddings, users_to_test, is_val, drop_flag=Fa
     test_users = list(users_to_test)
     n_test_users = len(test_users)
     u_batch_size = BATCH_SIZE * 2                                             # batch_test.py:117
+    if ops.SCORE_MODE.get(getattr(get_args(), "proj_mode", "3xtf32"), 0) != 2:
+        u_batch_size = max(u_batch_size, 32768)       # no score block is materialised: larger user blocks, same results
     truth = data_generator.val_set if is_val else data_generator.test_set
     ua = ua_embeddings.detach()
     ia = ia_embeddings.detach()

@@ -75,12 +75,21 @@ class Data(object):
         self._native = None
 
     # -- matrices ---------------------------------------------------------------------------------
-    def csr(self, which="train"):
-        """(rowptr int32[n_users+1], col int32[nnz]) of train_items / test_set / val_set."""
+    def csr(self, which="train", sorted_rows=False):
+        """(rowptr int32[n_users+1], col int32[nnz]) of train_items / test_set / val_set.  Rows keep the JSON order
+        (the sampler indexes into them); sorted_rows=True returns a copy with every row ascending (device masks)."""
         if which not in self._csr:
             src = {"train": self.train_items, "test": self.test_set, "val": self.val_set}[which]
             self._csr[which] = _csr_from_dict(src, self.n_users)
-        return self._csr[which]
+        if not sorted_rows:
+            return self._csr[which]
+        key = which + ":sorted"
+        if key not in self._csr:
+            rp, col = self._csr[which]
+            rows = np.repeat(np.arange(self.n_users), np.diff(rp))
+            order = np.lexsort((col, rows))
+            self._csr[key] = (rp, np.ascontiguousarray(col[order]))
+        return self._csr[key]
 
     @property
     def R(self):
