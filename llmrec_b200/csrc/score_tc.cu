@@ -67,9 +67,9 @@ __global__ void __launch_bounds__(384, 1) score_topk_tc_kernel(const __grid_cons
   constexpr uint32_t kTileB = SBN * SBK * 4;  // 16 KiB per hi or lo k-block
   const uint32_t stage_bytes = 2 * kTileB;
   uint8_t* ring = smem;
-  float* lv = reinterpret_cast<float*>(smem + (size_t)stages * stage_bytes);  // candidate values [Kc][128]
-  int* li = reinterpret_cast<int*>(lv + (size_t)Kc * SBM);                     // candidate ids    [Kc][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(li + (size_t)Kc * SBM);
+  float* lv = reinterpret_cast<float*>(smem + (size_t)stages * stage_bytes);  // candidate values [128][Kc+1]
+  int* li = reinterpret_cast<int*>(lv + (size_t)(Kc + 1) * SBM);               // candidate ids    [128][Kc+1]
+  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(li + (size_t)(Kc + 1) * SBM) + 15) & ~uintptr_t(15));
   uint64_t* full = bars; uint64_t* empty = bars + stages; uint64_t* tfull = bars + 2 * stages; uint64_t* tempty = tfull + 2;
   uint64_t* a_ready = tempty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 1);
@@ -174,17 +174,43 @@ __global__ void __launch_bounds__(384, 1) score_topk_tc_kernel(const __grid_cons
       while (mp < mend && P.mask_col[mp] < first_item) ++mp;   // rows are sorted; skip items of earlier slices
       next_masked = mp < mend ? P.mask_col[mp] : 0x7fffffff;
     }
-    int count = 0, min_pos = 0, min_id = -1;
+    // per-thread candidate list in shared memory, row layout [user][Kc+1] (odd stride: conflict-free both for the
+    // owner's single-element writes and for the warp-cooperative min scan over one user's list)
+    const int LS = Kc + 1;
+    float* wv = lv + (size_t)(wq * 32) * LS;     // this warp's 32 lists
+    int* wi = li + (size_t)(wq * 32) * LS;
+    int count = 0, min_pos = 0;
     float thr = -INFINITY;
-    float* myv = lv + t_in;
-    int* myi = li + t_in;
-    auto rescan = [&]() {
-      float mv = myv[0]; int mid = myi[0]; int mpos = 0;
-      for (int k = 1; k < Kc; ++k) {
-        const float v = myv[(size_t)k * SBM]; const int id = myi[(size_t)k * SBM];
-        if (v < mv || (v == mv && id > mid)) { mv = v; mid = id; mpos = k; }
+    // Insert (s, item) into lane `src`'s list; the WHOLE warp cooperates: 32 lanes scan the list for the new minimum
+    // under (score asc, id desc) with shuffles, instead of one divergent lane walking Kc entries alone.
+    auto coop_insert = [&](int src, float s, int item) {
+      const float ss = __shfl_sync(0xffffffffu, s, src);
+      const int it = __shfl_sync(0xffffffffu, item, src);
+      const int cnt = __shfl_sync(0xffffffffu, count, src);
+      const int mpos = __shfl_sync(0xffffffffu, min_pos, src);
+      float* pv = wv + (size_t)src * LS; int* pi = wi + (size_t)src * LS;
+      const int slot = cnt < Kc ? cnt : mpos;
+      if (lane == 0) { pv[slot] = ss; pi[slot] = it; }
+      __syncwarp();
+      const int ncnt = cnt < Kc ? cnt + 1 : cnt;
+      float mv = INFINITY; int mid = -1, mps = 0;
+      if (ncnt == Kc) {
+        for (int k = lane; k < Kc; k += 32) {
+          const float v = pv[k]; const int id = pi[k];
+          if (v < mv || (v == mv && id > mid)) { mv = v; mid = id; mps = k; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, mv, o); const int oid = __shfl_xor_sync(0xffffffffu, mid, o);
+          const int op = __shfl_xor_sync(0xffffffffu, mps, o);
+          if (ov < mv || (ov == mv && oid > mid)) { mv = ov; mid = oid; mps = op; }
+        }
       }
-      thr = mv; min_id = mid; min_pos = mpos;
+      if (lane == src) {
+        count = ncnt;
+        if (ncnt == Kc) { thr = mv; min_pos = mps; }
+      }
+      __syncwarp();
     };
     int acc = 0; uint32_t acc_phase = 0;
     for (int t = tile0; t < tile1; ++t) {
@@ -196,24 +222,25 @@ __global__ void __launch_bounds__(384, 1) score_topk_tc_kernel(const __grid_cons
         uint32_t r[32];
         tmem_ld_32x32(t0 + c0, r);
         tmem_ld_wait();
-        if (live) {
-          const int item0 = t * SBN + c0;
+        const int item0 = t * SBN + c0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int item = item0 + j;
-            const float s = __uint_as_float(r[j]);
+        for (int j = 0; j < 32; ++j) {
+          const int item = item0 + j;
+          const float s = __uint_as_float(r[j]);
+          bool want = false;
+          if (live) {
             if (item == next_masked) {  // train item: excluded from the candidates (batch_test.py:100-102)
               ++mp;
               next_masked = mp < mend ? P.mask_col[mp] : 0x7fffffff;
             } else if (item < P.n_items) {
-              if (count < Kc) {
-                myv[(size_t)count * SBM] = s; myi[(size_t)count * SBM] = item;
-                if (++count == Kc) rescan();
-              } else if (s > thr) {       // strict: an equal score with a larger id never displaces
-                myv[(size_t)min_pos * SBM] = s; myi[(size_t)min_pos * SBM] = item;
-                rescan();
-              }
+              want = (count < Kc) || (s > thr);   // strict: an equal score with a larger id never displaces
             }
+          }
+          unsigned m = __ballot_sync(0xffffffffu, want);
+          while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            coop_insert(src, s, item);
           }
         }
       }
@@ -222,16 +249,17 @@ __global__ void __launch_bounds__(384, 1) score_topk_tc_kernel(const __grid_cons
       if (lane == 0) mbar_arrive(&tempty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    const float* myv = wv + (size_t)lane * LS;
+    const int* myi = wi + (size_t)lane * LS;
     if (live) {
       int* oi = P.cand_idx + ((long long)b * P.splits + split) * Kc;
       float* ov = P.cand_val + ((long long)b * P.splits + split) * Kc;
       for (int k = 0; k < Kc; ++k) {
         const bool has = k < count;
-        oi[k] = has ? myi[(size_t)k * SBM] : -1;
-        ov[k] = has ? myv[(size_t)k * SBM] : -INFINITY;
+        oi[k] = has ? myi[k] : -1;
+        ov[k] = has ? myv[k] : -INFINITY;
       }
     }
-    (void)min_id;
   }
   tc_fence_before();
   __syncthreads();
@@ -340,7 +368,7 @@ int score_topk_tc(const float* U, long long ldu, const float* I, long long ldi, 
   P.U = U; P.ldu = ldu; P.users = users; P.n_batch = n_batch; P.n_items = n_items; P.d = d;
   P.mask_rowptr = mask_rowptr; P.mask_col = mask_col; P.cand_idx = cidx; P.cand_val = cval;
   P.tmem_cols = 512;
-  const size_t list_bytes = (size_t)P.Kc * SBM * 8;
+  const size_t list_bytes = (size_t)(P.Kc + 1) * SBM * 8 + 16;
   int stages = (int)((215 * 1024 - list_bytes - 512) / (2 * 16384));
   if (stages > 6) stages = 6;
   LLMREC_CHECK_ARG(stages >= 2, "score_topk: not enough shared memory for the pipeline");
