@@ -129,10 +129,10 @@ def run_ours(a):
                                 "--weight_size", wsize, "--proj_mode", a.proj_mode, "--host_sampler", a.host_sampler, "--cuda_graph", str(a.graph)]))
     torch.cuda.set_device(0)
     M.set_seed(args.seed)
-    gen = Data(path=resolve_dataset_dir(args.data_path, args.dataset), batch_size=args.batch_size, sampler=args.host_sampler)
-    batch_test.init(gen, args)
-    import io, contextlib
-    with contextlib.redirect_stdout(io.StringIO()):
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):          # stdout carries exactly one JSON line
+        gen = Data(path=resolve_dataset_dir(args.data_path, args.dataset), batch_size=args.batch_size, sampler=args.host_sampler)
+        batch_test.init(gen, args)
         tr = M.Trainer(data_config={}, data_generator=gen)
     hp = tr.hot
     K, W = a.steps, max(a.warmup, 3)

@@ -18,6 +18,7 @@
 //     order -- the same arithmetic as the SIMT reference kernel -- and emits the final top-K by (score desc, id asc), so
 //     the 3xTF32 rounding of the selection pass (~1e-5 relative) cannot change the result unless it misranks by more
 //     than the slack.
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -34,7 +35,7 @@ struct ScoreParams {
   const float* U; long long ldu;
   const int* users; int n_batch, n_items, d;
   const int* mask_rowptr; const int* mask_col;  // train rows, columns sorted ascending
-  int Kc, splits, tiles_per_split, stages, tmem_cols;
+  int Kc, splits, tiles_per_split, stages, tmem_cols, debug;
   int* cand_idx; float* cand_val;  // [n_batch][splits][Kc]
 };
 
@@ -67,9 +68,9 @@ __global__ void __launch_bounds__(384, 1) score_topk_tc_kernel(const __grid_cons
   constexpr uint32_t kTileB = SBN * SBK * 4;  // 16 KiB per hi or lo k-block
   const uint32_t stage_bytes = 2 * kTileB;
   uint8_t* ring = smem;
-  float* lv = reinterpret_cast<float*>(smem + (size_t)stages * stage_bytes);  // candidate values [128][Kc+1]
-  int* li = reinterpret_cast<int*>(lv + (size_t)(Kc + 1) * SBM);               // candidate ids    [128][Kc+1]
-  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(li + (size_t)(Kc + 1) * SBM) + 15) & ~uintptr_t(15));
+  float* lv = reinterpret_cast<float*>(smem + (size_t)stages * stage_bytes);  // heap values [Kc][128]
+  int* li = reinterpret_cast<int*>(lv + (size_t)Kc * SBM);                     // heap ids    [Kc][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(li + (size_t)Kc * SBM);
   uint64_t* full = bars; uint64_t* empty = bars + stages; uint64_t* tfull = bars + 2 * stages; uint64_t* tempty = tfull + 2;
   uint64_t* a_ready = tempty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 1);
@@ -166,51 +167,59 @@ __global__ void __launch_bounds__(384, 1) score_topk_tc_kernel(const __grid_cons
     const int t_in = wq * 32 + lane;  // row inside the tile == TMEM lane
     const int b = utile * SBM + t_in;
     const bool live = b < P.n_batch;
-    int mp = 0, mend = 0, next_masked = 0x7fffffff;
+    int mp = 0, mend = 0;
     if (live && P.mask_rowptr) {
       const int u = P.users[b];
       mp = P.mask_rowptr[u]; mend = P.mask_rowptr[u + 1];
-      const int first_item = tile0 * SBN;
-      while (mp < mend && P.mask_col[mp] < first_item) ++mp;   // rows are sorted; skip items of earlier slices
-      next_masked = mp < mend ? P.mask_col[mp] : 0x7fffffff;
     }
-    // per-thread candidate list in shared memory, row layout [user][Kc+1] (odd stride: conflict-free both for the
-    // owner's single-element writes and for the warp-cooperative min scan over one user's list)
-    const int LS = Kc + 1;
-    float* wv = lv + (size_t)(wq * 32) * LS;     // this warp's 32 lists
-    int* wi = li + (size_t)(wq * 32) * LS;
-    int count = 0, min_pos = 0;
-    float thr = -INFINITY;
-    // Insert (s, item) into lane `src`'s list; the WHOLE warp cooperates: 32 lanes scan the list for the new minimum
-    // under (score asc, id desc) with shuffles, instead of one divergent lane walking Kc entries alone.
-    auto coop_insert = [&](int src, float s, int item) {
-      const float ss = __shfl_sync(0xffffffffu, s, src);
-      const int it = __shfl_sync(0xffffffffu, item, src);
-      const int cnt = __shfl_sync(0xffffffffu, count, src);
-      const int mpos = __shfl_sync(0xffffffffu, min_pos, src);
-      float* pv = wv + (size_t)src * LS; int* pi = wi + (size_t)src * LS;
-      const int slot = cnt < Kc ? cnt : mpos;
-      if (lane == 0) { pv[slot] = ss; pi[slot] = it; }
-      __syncwarp();
-      const int ncnt = cnt < Kc ? cnt + 1 : cnt;
-      float mv = INFINITY; int mid = -1, mps = 0;
-      if (ncnt == Kc) {
-        for (int k = lane; k < Kc; k += 32) {
-          const float v = pv[k]; const int id = pi[k];
-          if (v < mv || (v == mv && id > mid)) { mv = v; mid = id; mps = k; }
+    // Per-thread binary MIN-heap of the K' best (score, id) seen so far, in shared memory with layout [k][thread]
+    // (bank = thread for every k: conflict-free however the heap paths of the 32 lanes diverge).  Heap order: a is
+    // "smaller" than b when a.score < b.score, or equal scores and a.id > b.id, so the root is the entry to evict and a
+    // new item enters only when strictly better than the root -> ties keep the lower item id.
+    float* hv = lv + t_in;
+    int* hi_ = li + t_in;
+    auto HV = [&](int k) -> float& { return hv[(size_t)k * SBM]; };
+    auto HI = [&](int k) -> int& { return hi_[(size_t)k * SBM]; };
+    auto lower = [](float av, int ai, float bv, int bi) { return av < bv || (av == bv && ai > bi); };
+    int count = 0;
+    float thr = -INFINITY;   // root score once the heap is full
+    int thr_id = -1;
+    auto sift_down = [&](int pos, float v, int id, int n) {
+      for (;;) {
+        int c = 2 * pos + 1;
+        if (c >= n) break;
+        float cv = HV(c); int ci = HI(c);
+        if (c + 1 < n) {
+          const float rv = HV(c + 1); const int ri = HI(c + 1);
+          if (lower(rv, ri, cv, ci)) { ++c; cv = rv; ci = ri; }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const float ov = __shfl_xor_sync(0xffffffffu, mv, o); const int oid = __shfl_xor_sync(0xffffffffu, mid, o);
-          const int op = __shfl_xor_sync(0xffffffffu, mps, o);
-          if (ov < mv || (ov == mv && oid > mid)) { mv = ov; mid = oid; mps = op; }
+        if (!lower(cv, ci, v, id)) break;
+        HV(pos) = cv; HI(pos) = ci;
+        pos = c;
+      }
+      HV(pos) = v; HI(pos) = id;
+    };
+    auto is_masked = [&](int item) -> bool {   // binary search in the user's sorted train row (slow path only)
+      int lo_ = mp, hi2 = mend;
+      while (lo_ < hi2) {
+        const int mid = (lo_ + hi2) >> 1;
+        const int v = __ldg(P.mask_col + mid);
+        if (v < item) lo_ = mid + 1; else hi2 = mid;
+      }
+      return lo_ < mend && __ldg(P.mask_col + lo_) == item;
+    };
+    auto offer = [&](float s, int item) {
+      if (item >= P.n_items || is_masked(item)) return;
+      if (count < Kc) {
+        HV(count) = s; HI(count) = item;
+        if (++count == Kc) {
+          for (int p = Kc / 2 - 1; p >= 0; --p) sift_down(p, HV(p), HI(p), Kc);   // heapify once
+          thr = HV(0); thr_id = HI(0);
         }
+      } else if (s > thr) {   // (equal score, larger id) never displaces: lowest id wins ties
+        sift_down(0, s, item, Kc);
+        thr = HV(0); thr_id = HI(0);
       }
-      if (lane == src) {
-        count = ncnt;
-        if (ncnt == Kc) { thr = mv; min_pos = mps; }
-      }
-      __syncwarp();
     };
     int acc = 0; uint32_t acc_phase = 0;
     for (int t = tile0; t < tile1; ++t) {
@@ -222,25 +231,20 @@ __global__ void __launch_bounds__(384, 1) score_topk_tc_kernel(const __grid_cons
         uint32_t r[32];
         tmem_ld_32x32(t0 + c0, r);
         tmem_ld_wait();
-        const int item0 = t * SBN + c0;
+        if (P.debug == 1) continue;   // profiling aid: pipeline without the selection
+        // fast path: one compare per score builds the mask of columns that beat the current threshold
+        unsigned hit = 0;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int item = item0 + j;
-          const float s = __uint_as_float(r[j]);
-          bool want = false;
-          if (live) {
-            if (item == next_masked) {  // train item: excluded from the candidates (batch_test.py:100-102)
-              ++mp;
-              next_masked = mp < mend ? P.mask_col[mp] : 0x7fffffff;
-            } else if (item < P.n_items) {
-              want = (count < Kc) || (s > thr);   // strict: an equal score with a larger id never displaces
+        for (int j = 0; j < 32; ++j) hit |= (__uint_as_float(r[j]) > thr ? 1u : 0u) << j;
+        if (!live || P.debug == 2) hit = 0;
+        const int item0 = t * SBN + c0;
+        if (hit) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {   // unrolled so r[j] stays in registers; order = ascending item id
+            if ((hit >> j) & 1u) {
+              const float s = __uint_as_float(r[j]);
+              if (count < Kc || s > thr) offer(s, item0 + j);
             }
-          }
-          unsigned m = __ballot_sync(0xffffffffu, want);
-          while (m) {
-            const int src = __ffs(m) - 1;
-            m &= m - 1;
-            coop_insert(src, s, item);
           }
         }
       }
@@ -249,15 +253,14 @@ __global__ void __launch_bounds__(384, 1) score_topk_tc_kernel(const __grid_cons
       if (lane == 0) mbar_arrive(&tempty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    const float* myv = wv + (size_t)lane * LS;
-    const int* myi = wi + (size_t)lane * LS;
+    (void)thr_id;
     if (live) {
       int* oi = P.cand_idx + ((long long)b * P.splits + split) * Kc;
       float* ov = P.cand_val + ((long long)b * P.splits + split) * Kc;
       for (int k = 0; k < Kc; ++k) {
         const bool has = k < count;
-        oi[k] = has ? myi[k] : -1;
-        ov[k] = has ? myv[k] : -INFINITY;
+        oi[k] = has ? HI(k) : -1;
+        ov[k] = has ? HV(k) : -INFINITY;
       }
     }
   }
@@ -275,50 +278,54 @@ __global__ void split_hi_lo_kernel(const float* __restrict__ X, long long ldx, l
   hi[i] = h; lo[i] = v - h;
 }
 
-// exact fp32 rescoring of the candidates of one user + final (score desc, id asc) top-K
+// exact fp32 rescoring of the candidates of one user + final (score desc, id asc) top-K: ONE WARP per user
+constexpr int kMaxCandPerLane = 20;   // 32 x 20 = 640 candidates (<= 6 slices x 96)
 __global__ void __launch_bounds__(256) rescore_topk_kernel(const float* __restrict__ U, long long ldu, const float* __restrict__ I, long long ldi,
-                                                           const int* __restrict__ users, int d, const int* __restrict__ cand_idx, int n_cand,
-                                                           int K, int* __restrict__ out_idx, float* __restrict__ out_val) {
-  extern __shared__ float sm[];  // d (user row) + n_cand (scores)
-  float* us = sm; float* sc = sm + d;
-  __shared__ float bv[8]; __shared__ int bi[8]; __shared__ int bp[8];
-  const int b = blockIdx.x;
+                                                           const int* __restrict__ users, int n_batch, int d, const int* __restrict__ cand_idx,
+                                                           int n_cand, int K, int* __restrict__ out_idx, float* __restrict__ out_val) {
+  extern __shared__ float sm[];  // 8 warps x d
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int b = blockIdx.x * 8 + w;
+  if (b >= n_batch) return;
+  float* us = sm + (size_t)w * d;
   const float* u = U + (long long)users[b] * ldu;
-  for (int j = threadIdx.x; j < d; j += blockDim.x) us[j] = u[j];
-  __syncthreads();
+  for (int j = lane; j < d; j += 32) us[j] = u[j];
+  __syncwarp();
   const int* ci = cand_idx + (long long)b * n_cand;
-  for (int c = threadIdx.x; c < n_cand; c += blockDim.x) {
-    const int item = ci[c];
+  float sc[kMaxCandPerLane]; int id[kMaxCandPerLane];
+#pragma unroll
+  for (int q = 0; q < kMaxCandPerLane; ++q) {
+    const int c = q * 32 + lane;
+    int item = c < n_cand ? ci[c] : -1;
     float a = -INFINITY;
     if (item >= 0) {
       const float* it = I + (long long)item * ldi;
       a = 0.f;
       for (int j = 0; j < d; ++j) a = fmaf(us[j], it[j], a);   // same order as score_rows_kernel (score_simt.cu)
     }
-    sc[c] = a;
+    sc[q] = a; id[q] = item;
   }
-  __syncthreads();
   for (int r = 0; r < K; ++r) {
-    float best = -INFINITY; int besti = 0x7fffffff, bestp = -1;
-    for (int c = threadIdx.x; c < n_cand; c += blockDim.x) {
-      const float v = sc[c]; const int id = ci[c];
-      if (id >= 0 && v != -INFINITY && (v > best || (v == best && id < besti))) { best = v; besti = id; bestp = c; }
+    float best = -INFINITY; int besti = 0x7fffffff, bestq = -1;
+#pragma unroll
+    for (int q = 0; q < kMaxCandPerLane; ++q) {
+      if (id[q] >= 0 && sc[q] != -INFINITY && (sc[q] > best || (sc[q] == best && id[q] < besti))) { best = sc[q]; besti = id[q]; bestq = q; }
     }
+    float wb = best; int wi = besti;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, besti, o); const int op = __shfl_xor_sync(0xffffffffu, bestp, o);
-      if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; bestp = op; }
+      const float ov = __shfl_xor_sync(0xffffffffu, wb, o); const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
+      if (ov > wb || (ov == wb && oi < wi)) { wb = ov; wi = oi; }
     }
-    if ((threadIdx.x & 31) == 0) { bv[threadIdx.x >> 5] = best; bi[threadIdx.x >> 5] = besti; bp[threadIdx.x >> 5] = bestp; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      for (int w = 1; w < 8; ++w) if (bv[w] > best || (bv[w] == best && bi[w] < besti)) { best = bv[w]; besti = bi[w]; bestp = bp[w]; }
-      const bool ok = bestp >= 0;
-      out_idx[(long long)b * K + r] = ok ? besti : -1;
-      if (out_val) out_val[(long long)b * K + r] = ok ? best : -INFINITY;
-      if (ok) sc[bestp] = -INFINITY;
+    const bool ok = wi != 0x7fffffff;
+    if (lane == 0) {
+      out_idx[(long long)b * K + r] = ok ? wi : -1;
+      if (out_val) out_val[(long long)b * K + r] = ok ? wb : -INFINITY;
     }
-    __syncthreads();
+    if (ok && bestq >= 0 && besti == wi) {   // the owning lane retires the winner (ids are unique per user)
+#pragma unroll
+      for (int q = 0; q < kMaxCandPerLane; ++q) if (q == bestq) id[q] = -1;
+    }
   }
 }
 
@@ -331,10 +338,10 @@ static int score_kc(int K) { int kc = ((K + 16 + 7) / 8) * 8; return kc > 96 ? 9
 static void score_plan(int n_batch, int n_items, int K, int* splits, int* tiles_per_split) {
   const int utiles = (n_batch + SBM - 1) / SBM;
   const int itiles = (n_items + SBN - 1) / SBN;
-  int s = (148 + utiles - 1) / utiles;          // fill the SMs when there are few user tiles
+  int s = utiles >= 74 ? 1 : (148 + utiles - 1) / utiles;   // cut the catalog only when user tiles cannot fill the SMs
   const int max_s = itiles / 32 > 0 ? itiles / 32 : 1;   // keep >= 4096 items per slice
   if (s > max_s) s = max_s;
-  if (s > 16) s = 16;
+  if (s > 6) s = 6;       // rescore_topk_kernel holds at most 32 x 20 candidates per user
   if (s < 1) s = 1;
   *tiles_per_split = (itiles + s - 1) / s;
   *splits = (itiles + *tiles_per_split - 1) / *tiles_per_split;
@@ -368,7 +375,8 @@ int score_topk_tc(const float* U, long long ldu, const float* I, long long ldi, 
   P.U = U; P.ldu = ldu; P.users = users; P.n_batch = n_batch; P.n_items = n_items; P.d = d;
   P.mask_rowptr = mask_rowptr; P.mask_col = mask_col; P.cand_idx = cidx; P.cand_val = cval;
   P.tmem_cols = 512;
-  const size_t list_bytes = (size_t)(P.Kc + 1) * SBM * 8 + 16;
+  P.debug = getenv("LLMREC_SCORE_DEBUG") ? atoi(getenv("LLMREC_SCORE_DEBUG")) : 0;
+  const size_t list_bytes = (size_t)P.Kc * SBM * 8;
   int stages = (int)((215 * 1024 - list_bytes - 512) / (2 * 16384));
   if (stages > 6) stages = 6;
   LLMREC_CHECK_ARG(stages >= 2, "score_topk: not enough shared memory for the pipeline");
@@ -379,7 +387,8 @@ int score_topk_tc(const float* U, long long ldu, const float* I, long long ldi, 
   score_topk_tc_kernel<<<grid, 384, smem, st>>>(P);
   LLMREC_CHECK_LAUNCH("score_topk_tc");
   const int n_cand = P.splits * P.Kc;
-  rescore_topk_kernel<<<n_batch, 256, (size_t)(d + n_cand) * sizeof(float), st>>>(U, ldu, I, ldi, users, d, cidx, n_cand, K, out_idx, out_val);
+  LLMREC_CHECK_ARG(n_cand <= 32 * kMaxCandPerLane, "score_topk: %d candidates per user exceed the rescoring capacity", n_cand);
+  rescore_topk_kernel<<<(n_batch + 7) / 8, 256, (size_t)8 * d * sizeof(float), st>>>(U, ldu, I, ldi, users, n_batch, d, cidx, n_cand, K, out_idx, out_val);
   LLMREC_CHECK_LAUNCH("rescore_topk");
   return 0;
 }

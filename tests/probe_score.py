@@ -5,7 +5,10 @@ import numpy as np, torch
 from llmrec_b200 import ops
 torch.manual_seed(0)
 dev = "cuda"
-for (nb, ni, d, K) in [(300, 1000, 64, 50), (200, 17366, 64, 50), (4096, 17366, 64, 50), (64, 100000, 128, 20), (1000, 5000, 32, 10)]:
+cases = [(300, 1000, 64, 50), (200, 17366, 64, 50), (4096, 17366, 64, 50), (64, 100000, 128, 20), (1000, 5000, 32, 10)]
+if len(sys.argv) > 1:
+    cases = [cases[int(sys.argv[1])]]
+for (nb, ni, d, K) in cases:
     nu = nb + 7
     U = torch.randn(nu, d, device=dev); I = torch.randn(ni, d, device=dev)
     users = torch.randperm(nu, device=dev)[:nb].to(torch.int32)
