@@ -167,10 +167,11 @@ __global__ void __launch_bounds__(384, 1) score_topk_tc_kernel(const __grid_cons
     const int t_in = wq * 32 + lane;  // row inside the tile == TMEM lane
     const int b = utile * SBM + t_in;
     const bool live = b < P.n_batch;
-    int mp = 0, mend = 0;
+    int mp = 0, mend = 0, next_masked = 0x7fffffff;
     if (live && P.mask_rowptr) {
       const int u = P.users[b];
       mp = P.mask_rowptr[u]; mend = P.mask_rowptr[u + 1];
+      next_masked = mp < mend ? __ldg(P.mask_col + mp) : 0x7fffffff;
     }
     // Per-thread binary MIN-heap of the K' best (score, id) seen so far, in shared memory with layout [k][thread]
     // (bank = thread for every k: conflict-free however the heap paths of the 32 lanes diverge).  Heap order: a is
@@ -199,14 +200,11 @@ __global__ void __launch_bounds__(384, 1) score_topk_tc_kernel(const __grid_cons
       }
       HV(pos) = v; HI(pos) = id;
     };
-    auto is_masked = [&](int item) -> bool {   // binary search in the user's sorted train row (slow path only)
-      int lo_ = mp, hi2 = mend;
-      while (lo_ < hi2) {
-        const int mid = (lo_ + hi2) >> 1;
-        const int v = __ldg(P.mask_col + mid);
-        if (v < item) lo_ = mid + 1; else hi2 = mid;
-      }
-      return lo_ < mend && __ldg(P.mask_col + lo_) == item;
+    // train-item test on the slow path only: merge pointer into the user's SORTED train row.  Offered items arrive in
+    // ascending id, so the pointer only moves forward; the usual case is one register compare, no memory access.
+    auto is_masked = [&](int item) -> bool {
+      while (next_masked < item) { ++mp; next_masked = mp < mend ? __ldg(P.mask_col + mp) : 0x7fffffff; }
+      return next_masked == item;
     };
     auto offer = [&](float s, int item) {
       if (item >= P.n_items || is_masked(item)) return;
