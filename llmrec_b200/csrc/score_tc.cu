@@ -70,7 +70,8 @@ __global__ void __launch_bounds__(384, 1) score_topk_tc_kernel(const __grid_cons
   uint8_t* ring = smem;
   float* lv = reinterpret_cast<float*>(smem + (size_t)stages * stage_bytes);  // heap values [Kc][128]
   int* li = reinterpret_cast<int*>(lv + (size_t)Kc * SBM);                     // heap ids    [Kc][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(li + (size_t)Kc * SBM);
+  float* scratch32 = reinterpret_cast<float*>(li + (size_t)Kc * SBM);          // [32][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(scratch32 + 32 * SBM);
   uint64_t* full = bars; uint64_t* empty = bars + stages; uint64_t* tfull = bars + 2 * stages; uint64_t* tempty = tfull + 2;
   uint64_t* a_ready = tempty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 1);
@@ -179,6 +180,7 @@ __global__ void __launch_bounds__(384, 1) score_topk_tc_kernel(const __grid_cons
     // new item enters only when strictly better than the root -> ties keep the lower item id.
     float* hv = lv + t_in;
     int* hi_ = li + t_in;
+    float* scr = scratch32 + t_in;   // [32][128] staging of one 32-column group
     auto HV = [&](int k) -> float& { return hv[(size_t)k * SBM]; };
     auto HI = [&](int k) -> int& { return hi_[(size_t)k * SBM]; };
     auto lower = [](float av, int ai, float bv, int bi) { return av < bv || (av == bv && ai > bi); };
@@ -237,12 +239,16 @@ __global__ void __launch_bounds__(384, 1) score_topk_tc_kernel(const __grid_cons
         if (!live || P.debug == 2) hit = 0;
         const int item0 = t * SBN + c0;
         if (hit) {
+          // slow path: park the 32 scores in this thread's scratch column and walk the set bits in ascending item id with
+          // ONE copy of the heap code (32 inlined copies overflowed the instruction cache)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {   // unrolled so r[j] stays in registers; order = ascending item id
-            if ((hit >> j) & 1u) {
-              const float s = __uint_as_float(r[j]);
-              if (count < Kc || s > thr) offer(s, item0 + j);
-            }
+          for (int j = 0; j < 32; ++j) scr[(size_t)j * SBM] = __uint_as_float(r[j]);
+          unsigned h = hit;
+          while (h) {
+            const int j = __ffs(h) - 1;
+            h &= h - 1;
+            const float s = scr[(size_t)j * SBM];
+            if (count < Kc || s > thr) offer(s, item0 + j);
           }
         }
       }
@@ -374,8 +380,8 @@ int score_topk_tc(const float* U, long long ldu, const float* I, long long ldi, 
   P.mask_rowptr = mask_rowptr; P.mask_col = mask_col; P.cand_idx = cidx; P.cand_val = cval;
   P.tmem_cols = 512;
   P.debug = getenv("LLMREC_SCORE_DEBUG") ? atoi(getenv("LLMREC_SCORE_DEBUG")) : 0;
-  const size_t list_bytes = (size_t)P.Kc * SBM * 8;
-  int stages = (int)((215 * 1024 - list_bytes - 512) / (2 * 16384));
+  const size_t list_bytes = (size_t)P.Kc * SBM * 8 + 32 * SBM * 4;
+  int stages = (int)((225 * 1024 - list_bytes - 512) / (2 * 16384));
   if (stages > 6) stages = 6;
   LLMREC_CHECK_ARG(stages >= 2, "score_topk: not enough shared memory for the pipeline");
   P.stages = stages;
