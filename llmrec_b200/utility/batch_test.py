@@ -72,7 +72,9 @@ def test_torch(ua_embeddings, ia_embeddings, users_to_test, is_val, drop_flag=Fa
         pending.append((user_batch, hits))
     for user_batch, hits in pending:                                          # one D2H per block, after all launches
         h = hits.cpu().numpy()
-        n_pos = np.fromiter((len(truth[u]) for u in user_batch), dtype=np.int64, count=len(user_batch))
+        trp = data_generator.csr("val" if is_val else "test")[0]
+        ub = np.asarray(user_batch, dtype=np.int64)
+        n_pos = (trp[ub + 1] - trp[ub]).astype(np.int64)                       # len(truth[u]) per user
         m = metrics.block_metrics(h, n_pos, Ks)
         for k in ("precision", "recall", "ndcg", "hit_ratio"):
             # sequential float64 accumulation in user order == the reference's `+= re[k] / n` loop (:160-165)

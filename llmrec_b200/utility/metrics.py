@@ -53,26 +53,41 @@ def auc(ground_truth, prediction):
         return 0.0
 
 
+_IDEAL_CACHE = {}
+
+
+def _ideal_dcg_table(K):
+    """best[m] = dcg_at_k of m ones followed by zeros, evaluated with the SAME numpy expression the scalar path uses."""
+    if K not in _IDEAL_CACHE:
+        disc = np.log2(np.arange(2, K + 2))
+        rows = (np.arange(K)[None, :] < np.arange(K + 1)[:, None]).astype(np.float64)
+        _IDEAL_CACHE[K] = np.array([np.sum(rows[m] / disc) for m in range(K + 1)])
+    return _IDEAL_CACHE[K]
+
+
 def block_metrics(hits, n_pos, Ks):
     """hits: uint8 [n x K_max] (rank order), n_pos: int [n] = len(test_set[u]).
-    Returns dict of float64 [n x len(Ks)] arrays: precision, recall, ndcg, hit_ratio."""
+    Returns dict of float64 [n x len(Ks)] arrays: precision, recall, ndcg, hit_ratio -- per user bit-identical to
+    precision_at_k / recall_at_k / ndcg_at_k / hit_at_k (hits are 0/1, so means and sums are exact integer ratios; the
+    ideal DCG of "m hits inside the retrieved list" comes from a table built with the scalar expression)."""
     hits = np.ascontiguousarray(hits)
-    n = hits.shape[0]
-    rf = hits.astype(np.float64)
-    ideal = -np.sort(-rf, axis=1)                                   # sorted(r, reverse=True)
+    n, kmax = hits.shape
     npos = np.asarray(n_pos, dtype=np.float64)
+    total_hits = hits.sum(axis=1, dtype=np.int64)                      # hits inside the whole retrieved list
     out = {k: np.zeros((n, len(Ks))) for k in ("precision", "recall", "ndcg", "hit_ratio")}
     for j, K in enumerate(Ks):
-        head_i = np.ascontiguousarray(hits[:, :K])
-        head = np.ascontiguousarray(rf[:, :K])
-        out["precision"][:, j] = np.mean(head_i, axis=1)
-        s = np.sum(head, axis=1)
+        K = min(K, kmax)
+        head = hits[:, :K]
+        cnt = head.sum(axis=1, dtype=np.int64)
+        cntf = cnt.astype(np.float64)
+        out["precision"][:, j] = cntf / K
         with np.errstate(divide="ignore", invalid="ignore"):
-            out["recall"][:, j] = np.where(npos == 0, 0.0, s / npos)
-        disc = np.log2(np.arange(2, head.shape[1] + 2))
-        dcg = np.sum(head / disc, axis=1)
-        best = np.sum(np.ascontiguousarray(ideal[:, :K]) / disc, axis=1)
-        with np.errstate(divide="ignore", invalid="ignore"):
-            out["ndcg"][:, j] = np.where(best == 0, 0.0, dcg / best)
-        out["hit_ratio"][:, j] = (np.sum(head_i, axis=1) > 0).astype(np.float64)
+            out["recall"][:, j] = np.where(npos == 0, 0.0, cntf / npos)
+        out["hit_ratio"][:, j] = (cnt > 0).astype(np.float64)
+        rows = np.nonzero(cnt)[0]                                      # dcg is 0 (and ndcg 0) without a hit in the head
+        if rows.size:
+            disc = np.log2(np.arange(2, K + 2))
+            dcg = np.sum(np.ascontiguousarray(head[rows]).astype(np.float64) / disc, axis=1)
+            best = _ideal_dcg_table(K)[np.minimum(total_hits[rows], K)]
+            out["ndcg"][rows, j] = dcg / best
     return out
