@@ -21,19 +21,17 @@
 // 32-byte atoms = UMMA layout SWIZZLE_128B_BASE32B / TMA SWIZZLE_128B_ATOM_32B, the one layout tcgen05 takes for
 // MN-major tf32) fetched as 32x32 TMA boxes -- no transpose pass over X or dY is ever materialised.
 #include <mutex>
+#include <stdlib.h>
 #include <vector>
 #include <string.h>
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "proj_tc.cuh"
 
 namespace llmrec {
 
 using namespace tc;
 
-constexpr int kMaxProb = 8;
-constexpr int BM = 128;  // tile rows (fwd) / tile features (wgrad) = UMMA M
-constexpr int BK = 32;   // fp32 per 128-byte swizzle row
-constexpr uint32_t kTileA = BM * BK * 4;  // 16 KiB
 
 // ------------------------------------------------------------------------------------------------
 // host: tensor maps
@@ -83,14 +81,6 @@ bool make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t inner, uint64
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-struct FwdProblem { int n, k, kblocks, tile_start; long long ldy; float* Y; const float* bias; };
-struct FwdParams {
-  CUtensorMap tmA[kMaxProb];
-  CUtensorMap tmW[kMaxProb];  // [2d x k] (hi rows then lo rows) when SPLIT, [d x k] otherwise
-  FwdProblem prob[kMaxProb];
-  int n_prob, total_tiles, d, stages, tmem_cols;
-};
-
 template <bool SPLIT>
 __global__ void __launch_bounds__(384, 1) proj_fwd_tc_kernel(const __grid_constant__ FwdParams P) {
   extern __shared__ uint8_t smem_raw[];
@@ -256,15 +246,6 @@ static uint32_t pow2_cols(int c) { uint32_t r = 32; while ((int)r < c) r <<= 1; 
 // ------------------------------------------------------------------------------------------------
 // wgrad
 // ------------------------------------------------------------------------------------------------
-struct WgProblem { int n, k, ft_tiles, chunks, rows_per_chunk, item_start; };
-struct WgParams {
-  CUtensorMap tmX[kMaxProb];
-  CUtensorMap tmG[kMaxProb];
-  WgProblem prob[kMaxProb];
-  int n_prob, total_items, d, stages, tmem_cols;
-  float* partial;  // [total_items][128][d]
-};
-
 template <bool SPLIT>
 __global__ void __launch_bounds__(384, 1) proj_wgrad_tc_kernel(const __grid_constant__ WgParams P) {
   extern __shared__ uint8_t smem_raw[];
@@ -532,6 +513,8 @@ int proj_fwd_tc_group(const llmrec_proj_fwd_problem* pr, int n_prob, int d, int 
   P.tmem_cols = (int)pow2_cols(2 * d);
   int grid = tiles < 148 ? tiles : 148;
   if (grid <= 0) return 0;
+  static const bool force_v1 = getenv("LLMREC_PROJ_V1") != nullptr;
+  if (split && d <= 128 && !force_v1) return proj_fwd_ts_launch(P, grid, st);   // A operand from tensor memory (proj_tc2.cu)
   if (split) {
     cudaFuncSetAttribute(proj_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     proj_fwd_tc_kernel<true><<<grid, 384, smem, st>>>(P);
@@ -588,7 +571,11 @@ int proj_wgrad_tc_group(const llmrec_proj_wgrad_problem* pr, int n_prob, int d, 
   P.tmem_cols = (int)pow2_cols(2 * d);
   int grid = items < 148 ? items : 148;
   if (grid <= 0) return 0;
-  if (split) {
+  static const bool force_v1 = getenv("LLMREC_PROJ_V1") != nullptr;
+  if (split && d <= 128 && !force_v1) {
+    int rc = proj_wgrad_ts_launch(P, grid, st);
+    if (rc) return rc;
+  } else if (split) {
     cudaFuncSetAttribute(proj_wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     proj_wgrad_tc_kernel<true><<<grid, 384, smem, st>>>(P);
   } else {
