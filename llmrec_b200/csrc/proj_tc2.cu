@@ -10,7 +10,8 @@
 //   forward  Y[n x d] = X W^T + b       A = X tile [128 rows x 32 k]  K-major in smem -> TMEM lane = row, column = k
 //   wgrad    dW^T[k x d] = X^T dY       A = X tile [32 rows x 128 feats] (MN-major atoms) -> TMEM lane = feature, column = row:
 //                                       the transposition the contraction needs happens in the smem -> TMEM copy, for free.
-// Warp roles, barriers, tile scheduling and epilogues are those of proj_tc.cu.  Supports d <= 128 (TMEM: 2 accumulators of
+// Warp roles (512 threads): w0 TMA | w1 MMA | w2 TMEM alloc | w4-7 + w12-15 two transform groups alternating k-blocks |
+// w8-11 epilogue; barriers, tile scheduling and epilogues are those of proj_tc.cu.  Supports d <= 128 (TMEM: 2 accumulators of
 // d columns + 4 ring slots of 64 columns); larger d falls back to v1.
 #include <string.h>
 #include "common.cuh"
@@ -22,7 +23,7 @@ using namespace tc;
 constexpr int kTsStages = 4;      // smem ring == TMEM A ring
 constexpr int kSlotCols = 64;     // hi 32 + lo 32 columns per ring slot
 
-__global__ void __launch_bounds__(384, 1) proj_fwd_ts_kernel(const __grid_constant__ FwdParams P) {
+__global__ void __launch_bounds__(512, 1) proj_fwd_ts_kernel(const __grid_constant__ FwdParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int d = P.d;
@@ -102,18 +103,24 @@ __global__ void __launch_bounds__(384, 1) proj_fwd_ts_kernel(const __grid_consta
       umma_commit(&tfull[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if ((warp >= 4 && warp < 8) || warp >= 12) {
     // ===== transform: smem A row -> registers -> split -> TMEM (lane = row of the tile) =====
-    PipeState st(stages);
+    // two warp-groups (warps 4-7: even k-blocks, warps 12-15: odd k-blocks) so that the LDS -> split -> tcgen05.st
+    // latency of one k-block overlaps the next one
+    const int grp = warp >= 12 ? 1 : 0;
     const int wq = warp & 3;
     const int row = wq * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16) + a_col0;
+    uint32_t it = 0;   // running k-block counter over all tiles of this CTA
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
       int p, mblk; locate(tile, p, mblk);
       const int kb_n = P.prob[p].kblocks;
-      for (int kb = 0; kb < kb_n; ++kb) {
-        mbar_wait(&full[st.stage], st.phase);
-        const uint8_t* rowp = sA(st.stage) + (size_t)row * 128;
+      for (int kb = 0; kb < kb_n; ++kb, ++it) {
+        if ((int)(it & 1u) != grp) continue;
+        const int stage = (int)(it % stages);
+        const uint32_t phase = (it / stages) & 1u;
+        mbar_wait(&full[stage], phase);
+        const uint8_t* rowp = sA(stage) + (size_t)row * 128;
         uint32_t hi[32], lo[32];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {  // logical 16-byte chunk c sits at physical chunk c ^ (row & 7) (SWIZZLE_128B)
@@ -123,15 +130,14 @@ __global__ void __launch_bounds__(384, 1) proj_fwd_ts_kernel(const __grid_consta
           lo[4 * c] = __float_as_uint(v.x - h0); lo[4 * c + 1] = __float_as_uint(v.y - h1);
           lo[4 * c + 2] = __float_as_uint(v.z - h2); lo[4 * c + 3] = __float_as_uint(v.w - h3);
         }
-        tmem_st_32x32(lane_base + (uint32_t)(st.stage * kSlotCols), hi);
-        tmem_st_32x32(lane_base + (uint32_t)(st.stage * kSlotCols + 32), lo);
+        tmem_st_32x32(lane_base + (uint32_t)(stage * kSlotCols), hi);
+        tmem_st_32x32(lane_base + (uint32_t)(stage * kSlotCols + 32), lo);
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&xform[st.stage]);
-        st.advance();
+        mbar_arrive(&xform[stage]);
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 8 && warp < 12) {
     const int wq = warp & 3;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
@@ -180,7 +186,7 @@ __global__ void __launch_bounds__(384, 1) proj_fwd_ts_kernel(const __grid_consta
   if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512u); }
 }
 
-__global__ void __launch_bounds__(384, 1) proj_wgrad_ts_kernel(const __grid_constant__ WgParams P) {
+__global__ void __launch_bounds__(512, 1) proj_wgrad_ts_kernel(const __grid_constant__ WgParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int d = P.d;
@@ -265,18 +271,23 @@ __global__ void __launch_bounds__(384, 1) proj_wgrad_ts_kernel(const __grid_cons
       umma_commit(&tfull[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if ((warp >= 4 && warp < 8) || warp >= 12) {
     // ===== transform: X tile column (one FEATURE over 32 rows) -> TMEM lane; dY tile split in place =====
-    PipeState st(stages);
+    // two warp-groups alternate k-blocks (see the forward kernel)
+    const int grp = warp >= 12 ? 1 : 0;
     const int wq = warp & 3;                          // feature atom: features [32*wq, 32*wq + 32)
     const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16) + a_col0;
-    const int tid = threadIdx.x - 128;
+    const int tid = (warp & 3) * 32 + lane;
+    uint32_t it = 0;
     for (int item = blockIdx.x; item < P.total_items; item += gridDim.x) {
       int p, ft, r0, kb_n; locate(item, p, ft, r0, kb_n);
-      for (int kb = 0; kb < kb_n; ++kb) {
-        mbar_wait(&full[st.stage], st.phase);
+      for (int kb = 0; kb < kb_n; ++kb, ++it) {
+        if ((int)(it & 1u) != grp) continue;
+        const int stage = (int)(it % stages);
+        const uint32_t phase = (it / stages) & 1u;
+        mbar_wait(&full[stage], phase);
         // element (row r, feature e = lane) of atom wq: byte r*128 + (((e >> 3) ^ (r & 3)) << 5) + (e & 7)*4   (SWIZZLE_128B_ATOM_32B)
-        const uint8_t* atom = sA(st.stage) + (size_t)wq * 4096;
+        const uint8_t* atom = sA(stage) + (size_t)wq * 4096;
         uint32_t hi[32], lo[32];
 #pragma unroll
         for (int r = 0; r < 32; ++r) {
@@ -284,17 +295,16 @@ __global__ void __launch_bounds__(384, 1) proj_wgrad_ts_kernel(const __grid_cons
           const float h = tf32_hi(v);
           hi[r] = __float_as_uint(h); lo[r] = __float_as_uint(v - h);
         }
-        tmem_st_32x32(lane_base + (uint32_t)(st.stage * kSlotCols), hi);
-        tmem_st_32x32(lane_base + (uint32_t)(st.stage * kSlotCols + 32), lo);
-        split_tile_inplace(reinterpret_cast<float4*>(sB(st.stage)), reinterpret_cast<float4*>(sBlo(st.stage)), (int)(b_bytes / 16), tid, 128);
+        tmem_st_32x32(lane_base + (uint32_t)(stage * kSlotCols), hi);
+        tmem_st_32x32(lane_base + (uint32_t)(stage * kSlotCols + 32), lo);
+        split_tile_inplace(reinterpret_cast<float4*>(sB(stage)), reinterpret_cast<float4*>(sBlo(stage)), (int)(b_bytes / 16), tid, 128);
         fence_proxy_async_smem();
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&xform[st.stage]);
-        st.advance();
+        mbar_arrive(&xform[stage]);
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 8 && warp < 12) {
     const int wq = warp & 3;
     int acc = 0; uint32_t acc_phase = 0;
     for (int item = blockIdx.x; item < P.total_items; item += gridDim.x) {
@@ -326,14 +336,14 @@ static uint32_t ts_smem_bytes(int d) { return (uint32_t)kTsStages * (kTileA + 2u
 int proj_fwd_ts_launch(const FwdParams& P, int grid, cudaStream_t st) {
   const uint32_t smem = ts_smem_bytes(P.d);
   cudaFuncSetAttribute(proj_fwd_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  proj_fwd_ts_kernel<<<grid, 384, smem, st>>>(P);
+  proj_fwd_ts_kernel<<<grid, 512, smem, st>>>(P);
   LLMREC_CHECK_LAUNCH("proj_fwd_ts");
   return 0;
 }
 int proj_wgrad_ts_launch(const WgParams& P, int grid, cudaStream_t st) {
   const uint32_t smem = ts_smem_bytes(P.d);
   cudaFuncSetAttribute(proj_wgrad_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  proj_wgrad_ts_kernel<<<grid, 384, smem, st>>>(P);
+  proj_wgrad_ts_kernel<<<grid, 512, smem, st>>>(P);
   LLMREC_CHECK_LAUNCH("proj_wgrad_ts");
   return 0;
 }
