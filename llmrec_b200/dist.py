@@ -50,7 +50,7 @@ def csr_from_sorted_rows(rows: torch.Tensor, n_rows: int) -> torch.Tensor:
     return rp.to(torch.int32)
 
 
-def build_shard_csr(u_local: torch.Tensor, items: torch.Tensor, nu_local: int, n_items: int, group=None):
+def build_shard_csr(u_local: torch.Tensor, items: torch.Tensor, nu_local: int, n_items: int, group=None, solo=False):
     """Device-agnostic part of the shard construction (also exercised on CPU with gloo in tests/test_dist_cpu.py):
     CSR(R_r), CSR(R_r^T) and the (deg + 1e-8)^-1/2 scales; ITEM degrees are summed over ranks."""
     key, _ = torch.sort(u_local.to(torch.int64) * n_items + items.to(torch.int64))
@@ -62,7 +62,7 @@ def build_shard_csr(u_local: torch.Tensor, items: torch.Tensor, nu_local: int, n
     col_i = (keyt % nu_local).to(torch.int32).contiguous()
     deg_u = (rowptr_u[1:] - rowptr_u[:-1]).to(torch.float64)
     deg_i = (rowptr_i[1:] - rowptr_i[:-1]).to(torch.float64)
-    if dist.is_initialized() and dist.get_world_size(group) > 1:
+    if not solo and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(deg_i, group=group)                             # item degrees are global
     inv = lambda d: torch.pow(d + 1e-8, -0.5).to(torch.float32)         # main.py:114-118 (never inf with the +1e-8)
     return dict(rowptr_u=rowptr_u, col_u=col_u, rowptr_i=rowptr_i, col_i=col_i, su=inv(deg_u), si=inv(deg_i), nnz=int(key.numel()))
@@ -71,8 +71,8 @@ def build_shard_csr(u_local: torch.Tensor, items: torch.Tensor, nu_local: int, n
 class ShardedGraph:
     """Local shard of the bipartite graph.  u_local/items: int64 edge lists (local user row, global item), unique pairs."""
 
-    def __init__(self, u_local: torch.Tensor, items: torch.Tensor, nu_local: int, n_items: int, group=None, tile_nnz: int = 0):
-        c = build_shard_csr(u_local, items, nu_local, n_items, group)
+    def __init__(self, u_local: torch.Tensor, items: torch.Tensor, nu_local: int, n_items: int, group=None, tile_nnz: int = 0, solo=False):
+        c = build_shard_csr(u_local, items, nu_local, n_items, group, solo)
         self.nu_local, self.n_items, self.nnz = int(nu_local), int(n_items), c["nnz"]
         self.su, self.si = c["su"], c["si"]
         rowptr_u, col_u, rowptr_i, col_i = c["rowptr_u"], c["col_u"], c["rowptr_i"], c["col_i"]
@@ -87,9 +87,9 @@ class ShardedGraph:
 class ShardedHotPath:
     """ID-only training step over a ShardedGraph; world size 1 reproduces engine.HotPath(feats=None) exactly."""
 
-    def __init__(self, graph: ShardedGraph, E_u_local: torch.Tensor, E_i: torch.Tensor, cfg: HotPathConfig, user_lo: int, group=None):
+    def __init__(self, graph: ShardedGraph, E_u_local: torch.Tensor, E_i: torch.Tensor, cfg: HotPathConfig, user_lo: int, group=None, solo=False):
         self.g, self.cfg, self.group = graph, cfg, group
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.world = dist.get_world_size(group) if (dist.is_initialized() and not solo) else 1
         self.E_u, self.E_i = E_u_local, E_i
         self.lo, self.hi = int(user_lo), int(user_lo) + E_u_local.shape[0]
         nu, ni, d, L = E_u_local.shape[0], E_i.shape[0], cfg.embed_size, cfg.n_layers

@@ -65,6 +65,7 @@ def run_sharded(a):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms)
     launches = ops.STATS["launches"] - l0
+    comm_per_step = hp.comm_bytes // K
     # end-to-end: batch indices start in pinned host memory every step, loss read back every step
     hb = [torch.stack([b.cpu() for b in batches[W + i]]).pin_memory() for i in range(K)]
     loss_host = torch.empty(K, dtype=torch.float32).pin_memory()
@@ -94,8 +95,9 @@ def run_sharded(a):
     e1.record(); torch.cuda.synchronize()
     t_spmm = e0.elapsed_time(e1) / 5
     nu_l = hi - lo
-    alg = 4 * g.nnz + 4 * (ni + 1) + 4 * d * nu_l + 4 * d * ni
-    gather = 4 * g.nnz + 4 * d * g.nnz + 4 * d * ni
+    nnz_local = g.nnz
+    alg = 4 * nnz_local + 4 * (ni + 1) + 4 * d * nu_l + 4 * d * ni
+    gather = 4 * nnz_local + 4 * d * nnz_local + 4 * d * ni
 
     # ---- full-catalog eval leg (BASELINE.json configs[4]): every rank ranks its own users against the replicated item table
     #      (users are independent: no exchange); tcgen05 scoring + fused top-K, train rows of the local shard as the mask
@@ -117,6 +119,33 @@ def run_sharded(a):
         dist.all_reduce(ms_ev, op=dist.ReduceOp.MAX)
     ms_ev = float(ms_ev)
     ok_mask = bool((top >= 0).all())
+    # ---- the SAME workload on ONE GPU (rank 0 alone, other ranks wait): the strong-scaling base measured in this run ----
+    base = None
+    if world > 1 and a.n1_base:
+        del hp, g, E_u, E_i, top, seg, eu
+        torch.cuda.empty_cache()
+        if rank == 0:
+            ul, it, lo1, hi1 = synthetic_shard(nu, ni, ne, 0, 1, dev, seed=0)
+            g1 = ShardedGraph(ul, it, nu, ni, solo=True)
+            del ul, it
+            torch.cuda.empty_cache()
+            Eu1 = (torch.rand(nu, d, device=dev, generator=torch.Generator(device=dev).manual_seed(77)) * 2 - 1) * bound
+            Ei1 = (torch.rand(ni, d, device=dev, generator=torch.Generator(device=dev).manual_seed(1234)) * 2 - 1) * (6.0 / (ni + d)) ** 0.5
+            hp1 = ShardedHotPath(g1, Eu1, Ei1, cfg, 0, solo=True)
+            k1 = max(3, min(K, 5))
+            for i in range(3):
+                hp1.train_step(*batches[i])
+            torch.cuda.synchronize()
+            e0.record()
+            for i in range(k1):
+                hp1.train_step(*batches[W + i])
+            e1.record(); torch.cuda.synchronize()
+            ms1 = e0.elapsed_time(e1)
+            base = {"n_gpus": 1, "value": round(B * k1 / (ms1 / 1e3), 1), "unit": "interactions/s", "ms_per_step": round(ms1 / k1, 4), "steps": k1,
+                    "note": "same synthetic workload, same code path, rank 0 alone (other ranks idle); edges of the 1-GPU graph are drawn with the 1-rank generator"}
+            del hp1, g1, Eu1, Ei1
+            torch.cuda.empty_cache()
+        dist.barrier()
     if rank != 0:
         return None
     import json
@@ -127,11 +156,11 @@ def run_sharded(a):
             "data": "synthetic", "impl": "ours",
             "config": {"workload": f"synthetic {nu}x{ni}, {int(nnz)} unique edges (Zipf 0.8 item popularity), d={d}, L={L}, global batch {B} triplets, "
                                    "ID propagation + BPR/prune + dense AdamW, no side features; users sharded over ranks, items replicated",
-                       "l2": "inputs larger than L2", "graph_build_s": round(build_s, 1), "allreduce_bytes_per_step": hp.comm_bytes // K,
+                       "l2": "inputs larger than L2", "graph_build_s": round(build_s, 1), "allreduce_bytes_per_step": comm_per_step,
                        "cuda_graph": False},
             "e2e": {"value": round(B * K / (ms2 / 1e3), 1), "unit": "interactions/s", "h2d_bytes_per_step": 3 * 4 * B, "d2h_bytes_per_step": 4,
                     "ms_per_step": round(ms2 / K, 4)},
-            "gpu_launches": launches,
+            "gpu_launches": launches, "same_workload_1gpu": base,
             "roofline": {"kernel": "spmm_tile_kernel (item-side gather R_r^T . U, one rank)", "bound": "hbm", "achieved": round(alg / (t_spmm * 1e-3) / 1e9, 1),
                          "peak": hbm, "unit": "GB/s", "frac": round(alg / (t_spmm * 1e-3) / 1e9 / hbm, 4), "traffic": None, "peak_source": src,
                          "alg_bytes": alg, "ms": round(t_spmm, 4), "gather_bound_gbs": round(gather / (t_spmm * 1e-3) / 1e9, 1),
