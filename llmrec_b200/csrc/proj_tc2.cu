@@ -20,14 +20,14 @@
 namespace llmrec {
 using namespace tc;
 
-constexpr int kTsStages = 4;      // smem ring == TMEM A ring
+constexpr int kTsMaxStages = 6;   // smem ring == TMEM A ring: 6 slots at d <= 64 (2d + 6*64 <= 512 columns, 6 x 32 KiB smem), else 4
 constexpr int kSlotCols = 64;     // hi 32 + lo 32 columns per ring slot
 
 __global__ void __launch_bounds__(512, 1) proj_fwd_ts_kernel(const __grid_constant__ FwdParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int d = P.d;
-  constexpr int stages = kTsStages;
+  const int stages = P.stages;
   const uint32_t b_bytes = (uint32_t)d * 128u;
   const uint32_t stage_bytes = kTileA + 2u * b_bytes;           // A fp32 | W_hi | W_lo
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(512, 1) proj_wgrad_ts_kernel(const __grid_cons
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int d = P.d;
-  constexpr int stages = kTsStages;
+  const int stages = P.stages;
   const uint32_t b_bytes = (uint32_t)d * 128u;                  // [d/32 atoms][32 rows][128 B]
   const uint32_t stage_bytes = kTileA + 2u * b_bytes;           // X tile fp32 | dY_hi (in place) | dY_lo
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
@@ -331,16 +331,22 @@ __global__ void __launch_bounds__(512, 1) proj_wgrad_ts_kernel(const __grid_cons
   if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512u); }
 }
 
-static uint32_t ts_smem_bytes(int d) { return (uint32_t)kTsStages * (kTileA + 2u * (uint32_t)d * 128u) + 1024 + 256; }
+// The ring must cover HBM latency + transform + MMA time of a stage (~2900 clk): 4 stages of 16 KiB sustain only ~3.5 TB/s.
+static int ts_stages(int d) { return d <= 64 ? kTsMaxStages : 4; }
+static uint32_t ts_smem_bytes(int d) { return (uint32_t)ts_stages(d) * (kTileA + 2u * (uint32_t)d * 128u) + 1024 + 256; }
 
-int proj_fwd_ts_launch(const FwdParams& P, int grid, cudaStream_t st) {
+int proj_fwd_ts_launch(const FwdParams& P0, int grid, cudaStream_t st) {
+  FwdParams P = P0;
+  P.stages = ts_stages(P.d);
   const uint32_t smem = ts_smem_bytes(P.d);
   cudaFuncSetAttribute(proj_fwd_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   proj_fwd_ts_kernel<<<grid, 512, smem, st>>>(P);
   LLMREC_CHECK_LAUNCH("proj_fwd_ts");
   return 0;
 }
-int proj_wgrad_ts_launch(const WgParams& P, int grid, cudaStream_t st) {
+int proj_wgrad_ts_launch(const WgParams& P0, int grid, cudaStream_t st) {
+  WgParams P = P0;
+  P.stages = ts_stages(P.d);
   const uint32_t smem = ts_smem_bytes(P.d);
   cudaFuncSetAttribute(proj_wgrad_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   proj_wgrad_ts_kernel<<<grid, 512, smem, st>>>(P);

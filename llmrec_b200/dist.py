@@ -71,7 +71,7 @@ def build_shard_csr(u_local: torch.Tensor, items: torch.Tensor, nu_local: int, n
 class ShardedGraph:
     """Local shard of the bipartite graph.  u_local/items: int64 edge lists (local user row, global item), unique pairs."""
 
-    def __init__(self, u_local: torch.Tensor, items: torch.Tensor, nu_local: int, n_items: int, group=None, tile_nnz: int = 0, solo=False):
+    def __init__(self, u_local: torch.Tensor, items: torch.Tensor, nu_local: int, n_items: int, group=None, tile_nnz: int = 0, solo=False, pieces: int = 1):
         c = build_shard_csr(u_local, items, nu_local, n_items, group, solo)
         self.nu_local, self.n_items, self.nnz = int(nu_local), int(n_items), c["nnz"]
         self.su, self.si = c["su"], c["si"]
@@ -80,8 +80,19 @@ class ShardedGraph:
         # ui: rows = local users (row scale su).  iu_raw / uiT_raw: rows = items, partial sums to be all-reduced.
         self.ui = CsrOperator(rowptr_u, col_u, nu_local, n_items, rs=self.su, tile_nnz=tile_nnz)
         self.iu_raw = CsrOperator(rowptr_i, col_i, n_items, nu_local, tile_nnz=tile_nnz)
-        self.uiT_raw = CsrOperator(rowptr_i, col_i, n_items, nu_local, vals=self.su[col_i.long()].contiguous(), plan=self.iu_raw.plan)
+        w_uiT = self.su[col_i.long()].contiguous()
+        self.uiT_raw = CsrOperator(rowptr_i, col_i, n_items, nu_local, vals=w_uiT, plan=self.iu_raw.plan)
         self.iuT = CsrOperator(rowptr_u, col_u, nu_local, n_items, vals=self.si[col_u.long()].contiguous(), plan=self.ui.plan)
+        # item-row pieces of the two exchange operators: piece k's all-reduce overlaps the SpMM of piece k+1
+        self.pieces = []
+        if pieces > 1:
+            b = shard_bounds(n_items, pieces)
+            for k in range(pieces):
+                lo, hi = b[k], b[k + 1]
+                rp = rowptr_i[lo:hi + 1].contiguous()
+                fwd = CsrOperator(rp, col_i, hi - lo, nu_local, tile_nnz=tile_nnz)
+                bwd = CsrOperator(rp, col_i, hi - lo, nu_local, vals=w_uiT, plan=fwd.plan)
+                self.pieces.append((lo, hi, fwd, bwd))
 
 
 class ShardedHotPath:
@@ -117,13 +128,29 @@ class ShardedHotPath:
             dist.all_reduce(t, group=self.group)
             self.comm_bytes += t.numel() * 4
 
+    def _exchange(self, which, src):
+        """self.part = sum over ranks of (item-side operator `which`) . src.  With item-row pieces, the NCCL all-reduce of
+        piece k runs on NCCL's stream while the SpMM of piece k+1 runs on the compute stream (NVLink transfer hidden
+        behind the gather)."""
+        g = self.g
+        if self.world == 1 or not g.pieces:
+            (g.iu_raw if which == "iu" else g.uiT_raw).apply([(src, self.part, None, False)])
+            self._allreduce(self.part)
+            return
+        works = []
+        for lo, hi, fwd, bwd in g.pieces:
+            (fwd if which == "iu" else bwd).apply([(src, self.part[lo:hi], None, False)])
+            works.append(dist.all_reduce(self.part[lo:hi], group=self.group, async_op=True))
+            self.comm_bytes += (hi - lo) * self.d * 4
+        for w in works:
+            w.wait()
+
     # -- forward (Models.py:169-186) ------------------------------------------------------------------------
     def forward(self):
         L = self.L
         for l in range(1, L + 1):
             self.g.ui.apply([(self.Il[l - 1], self.Ul[l], None, l == L)])                    # U_l = [softmax] ui . I_{l-1}
-            self.g.iu_raw.apply([(self.Ul[l], self.part, None, False)])                       # partial of R^T U_l
-            self._allreduce(self.part)
+            self._exchange("iu", self.Ul[l])                                                  # sum_r R_r^T U_l  (all-reduce)
             ops.row_scale_softmax(self.part, self.g.si, self.Il[l], l == L)                   # I_l = [softmax] si (.) sum
         ops.fuse_fwd(self.Ul, [], [], self.U)                                                 # mean over layers (:185-186)
         ops.fuse_fwd(self.Il, [], [], self.I)
@@ -161,8 +188,7 @@ class ShardedHotPath:
             self.g.iuT.apply([(src, self.bufU, self.g_Eu, False)])                            # gU_l = dUl + iu^T src   (local rows)
             if l == L:
                 ops.row_softmax_bwd(self.Ul[l], self.bufU, out=self.bufU)
-            self.g.uiT_raw.apply([(self.bufU, self.part, None, False)])                       # partial of ui^T gU_l
-            self._allreduce(self.part)
+            self._exchange("uiT", self.bufU)                                                  # sum_r R_r^T (su (.) gU_l)
             dst = self.g_Ei if l == 1 else self.bufI
             torch.add(self.part, self.dIl, out=dst)                                           # gI_{l-1} = dIl + sum
             g_cur = dst

@@ -26,7 +26,7 @@ def run_sharded(a):
     nu, ni, ne, d, L = int(10_000_000 * scale), int(1_000_000 * scale), int(200_000_000 * scale), 128, 2
     t0 = time.perf_counter()
     ul, it, lo, hi = synthetic_shard(nu, ni, ne, rank, world, dev, seed=0)
-    g = ShardedGraph(ul, it, hi - lo, ni)
+    g = ShardedGraph(ul, it, hi - lo, ni, pieces=(a.pieces if world > 1 else 1))
     del ul, it
     torch.cuda.empty_cache()
     gen = torch.Generator(device=dev).manual_seed(1234)
