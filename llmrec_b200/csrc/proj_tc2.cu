@@ -13,6 +13,7 @@
 // Warp roles (512 threads): w0 TMA | w1 MMA | w2 TMEM alloc | w4-7 + w12-15 two transform groups alternating k-blocks |
 // w8-11 epilogue; barriers, tile scheduling and epilogues are those of proj_tc.cu.  Supports d <= 128 (TMEM: 2 accumulators of
 // d columns + 4 ring slots of 64 columns); larger d falls back to v1.
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 #include "proj_tc.cuh"
@@ -29,7 +30,7 @@ __global__ void __launch_bounds__(512, 1) proj_fwd_ts_kernel(const __grid_consta
   const int d = P.d;
   const int stages = P.stages;
   const uint32_t b_bytes = (uint32_t)d * 128u;
-  const uint32_t stage_bytes = kTileA + 2u * b_bytes;           // A fp32 | W_hi | W_lo
+  const uint32_t stage_bytes = kTileA + 2u * b_bytes;           // A fp32 | W (-> W_hi in place) | W_lo
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
   uint64_t* full = bars; uint64_t* xform = bars + stages; uint64_t* empty = bars + 2 * stages;
   uint64_t* tfull = bars + 3 * stages; uint64_t* tempty = tfull + 2;
@@ -67,10 +68,9 @@ __global__ void __launch_bounds__(512, 1) proj_fwd_ts_kernel(const __grid_consta
       const int kb_n = P.prob[p].kblocks;
       for (int kb = 0; kb < kb_n; ++kb) {
         mbar_wait(&empty[st.stage], st.phase ^ 1);
-        mbar_arrive_expect_tx(&full[st.stage], stage_bytes);
+        mbar_arrive_expect_tx(&full[st.stage], kTileA + b_bytes);
         tma_load_2d(sA(st.stage), &P.tmA[p], &full[st.stage], kb * BK, mblk * BM);
-        tma_load_2d(sB(st.stage), &P.tmW[p], &full[st.stage], kb * BK, 0);
-        tma_load_2d(sBlo(st.stage), &P.tmW[p], &full[st.stage], kb * BK, d);
+        tma_load_2d(sB(st.stage), &P.tmW[p], &full[st.stage], kb * BK, 0);       // fp32 W tile; split in smem by the transform warps
         st.advance();
       }
     }
@@ -93,9 +93,9 @@ __global__ void __launch_bounds__(512, 1) proj_fwd_ts_kernel(const __grid_consta
         for (int kk = 0; kk < 4; ++kk) {
           const uint64_t bd = smem_desc_sw128(b0 + kk * 32, 0, 1024);
           const uint64_t bld = smem_desc_sw128(bl0 + kk * 32, 0, 1024);
-          umma_tf32_ts(d_tmem, a_lo + kk * 8, bd, idesc, (kb | kk) != 0);   // lo * hi
-          umma_tf32_ts(d_tmem, a_hi + kk * 8, bld, idesc, 1);                // hi * lo
-          umma_tf32_ts(d_tmem, a_hi + kk * 8, bd, idesc, 1);                 // hi * hi
+          if (P.tmem_cols != 1) umma_tf32_ts(d_tmem, a_lo + kk * 8, bd, idesc, (kb | kk) != 0);   // lo * hi
+          if (P.tmem_cols != 1 && P.tmem_cols != 2) umma_tf32_ts(d_tmem, a_hi + kk * 8, bld, idesc, 1);   // hi * lo
+          umma_tf32_ts(d_tmem, a_hi + kk * 8, bd, idesc, (P.tmem_cols == 1) ? (uint32_t)((kb | kk) != 0) : 1u);   // hi * hi
         }
         umma_commit(&empty[st.stage]);
         st.advance();
@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(512, 1) proj_fwd_ts_kernel(const __grid_consta
         const int stage = (int)(it % stages);
         const uint32_t phase = (it / stages) & 1u;
         mbar_wait(&full[stage], phase);
+        if (P.tmem_cols == 4) { mbar_arrive(&xform[stage]); continue; }   // profiling aid: no transform at all
         const uint8_t* rowp = sA(stage) + (size_t)row * 128;
         uint32_t hi[32], lo[32];
 #pragma unroll
@@ -130,8 +131,16 @@ __global__ void __launch_bounds__(512, 1) proj_fwd_ts_kernel(const __grid_consta
           lo[4 * c] = __float_as_uint(v.x - h0); lo[4 * c + 1] = __float_as_uint(v.y - h1);
           lo[4 * c + 2] = __float_as_uint(v.z - h2); lo[4 * c + 3] = __float_as_uint(v.w - h3);
         }
+        if (P.tmem_cols == 5) {   // profiling aid: LDS + split, no TMEM store
+          if (hi[0] == 0x7fc12345u && lo[31] == 0x7fc12345u) P.prob[0].Y[0] = 1.f;
+          mbar_arrive(&xform[stage]);
+          continue;
+        }
         tmem_st_32x32(lane_base + (uint32_t)(stage * kSlotCols), hi);
         tmem_st_32x32(lane_base + (uint32_t)(stage * kSlotCols + 32), lo);
+        // W tile -> W_hi (in place) + W_lo: halves the L2 -> SM traffic of the weights (they are re-read for every row tile)
+        split_tile_inplace(reinterpret_cast<float4*>(sB(stage)), reinterpret_cast<float4*>(sBlo(stage)), (int)(b_bytes / 16), row, 128);
+        fence_proxy_async_smem();
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&xform[stage]);
@@ -338,6 +347,7 @@ static uint32_t ts_smem_bytes(int d) { return (uint32_t)ts_stages(d) * (kTileA +
 int proj_fwd_ts_launch(const FwdParams& P0, int grid, cudaStream_t st) {
   FwdParams P = P0;
   P.stages = ts_stages(P.d);
+  P.tmem_cols = getenv("LLMREC_PROJ_DBG_MMAS") ? atoi(getenv("LLMREC_PROJ_DBG_MMAS")) : 3;   // profiling aid: 1 / 2 / 3 MMAs per K step
   const uint32_t smem = ts_smem_bytes(P.d);
   cudaFuncSetAttribute(proj_fwd_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   proj_fwd_ts_kernel<<<grid, 512, smem, st>>>(P);
