@@ -487,25 +487,22 @@ bool proj_tc_supported(int d, int64_t ldx, const void* X, int k, bool wgrad) {
 
 int proj_fwd_tc_group(const llmrec_proj_fwd_problem* pr, int n_prob, int d, int mode, cudaStream_t st) {
   const bool split = (mode == 0);
-  static const bool force_v1 = getenv("LLMREC_PROJ_V1") != nullptr;
-  const bool use_ts = split && d <= 128 && !force_v1;   // v2: A operand in TMEM, W split inside the kernel (proj_tc2.cu)
   FwdParams P;
   memset(&P, 0, sizeof(P));
   P.n_prob = n_prob; P.d = d;
   int tiles = 0;
   for (int p = 0; p < n_prob; ++p) {
-    const bool presplit = split && !use_ts;
-    const float* wsrc = presplit ? pr[p].wsplit : pr[p].W;
-    LLMREC_CHECK_ARG(!presplit || pr[p].wsplit, "proj_fwd: 3xTF32 mode needs a wsplit buffer of 2*d*k floats");
+    const float* wsrc = split ? pr[p].wsplit : pr[p].W;
+    LLMREC_CHECK_ARG(!split || pr[p].wsplit, "proj_fwd: 3xTF32 mode needs a wsplit buffer of 2*d*k floats");
     bool fresh = true;
     for (int q = 0; q < p; ++q) fresh = fresh && !(pr[q].W == pr[p].W && pr[q].wsplit == pr[p].wsplit);
-    if (presplit && fresh) {
+    if (split && fresh) {
       int64_t n = (int64_t)d * pr[p].k;
       wsplit_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pr[p].W, pr[p].wsplit, n);
       LLMREC_CHECK_LAUNCH("wsplit");
     }
     if (!make_tmap_2d_f32(&P.tmA[p], pr[p].X, (uint64_t)pr[p].k, (uint64_t)pr[p].n, (uint64_t)pr[p].ldx * 4, BK, BM)) return 4;
-    if (!make_tmap_2d_f32(&P.tmW[p], wsrc, (uint64_t)pr[p].k, (uint64_t)(presplit ? 2 * d : d), (uint64_t)pr[p].k * 4, BK, (uint32_t)d)) return 4;
+    if (!make_tmap_2d_f32(&P.tmW[p], wsrc, (uint64_t)pr[p].k, (uint64_t)(split ? 2 * d : d), (uint64_t)pr[p].k * 4, BK, (uint32_t)d)) return 4;
     P.prob[p].n = (int)pr[p].n; P.prob[p].k = pr[p].k; P.prob[p].kblocks = (pr[p].k + BK - 1) / BK;
     P.prob[p].tile_start = tiles; P.prob[p].ldy = pr[p].ldy; P.prob[p].Y = pr[p].Y; P.prob[p].bias = pr[p].bias;
     tiles += (int)((pr[p].n + BM - 1) / BM);
@@ -516,7 +513,8 @@ int proj_fwd_tc_group(const llmrec_proj_fwd_problem* pr, int n_prob, int d, int 
   P.tmem_cols = (int)pow2_cols(2 * d);
   int grid = tiles < 148 ? tiles : 148;
   if (grid <= 0) return 0;
-  if (use_ts) return proj_fwd_ts_launch(P, grid, st);
+  static const bool force_v1 = getenv("LLMREC_PROJ_V1") != nullptr;
+  if (split && d <= 128 && !force_v1) return proj_fwd_ts_launch(P, grid, st);   // A operand from tensor memory (proj_tc2.cu)
   if (split) {
     cudaFuncSetAttribute(proj_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     proj_fwd_tc_kernel<true><<<grid, 384, smem, st>>>(P);

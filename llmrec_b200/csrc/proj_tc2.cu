@@ -13,7 +13,6 @@
 // Warp roles (512 threads): w0 TMA | w1 MMA | w2 TMEM alloc | w4-7 + w12-15 two transform groups alternating k-blocks |
 // w8-11 epilogue; barriers, tile scheduling and epilogues are those of proj_tc.cu.  Supports d <= 128 (TMEM: 2 accumulators of
 // d columns + 4 ring slots of 64 columns); larger d falls back to v1.
-#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 #include "proj_tc.cuh"
@@ -30,7 +29,7 @@ __global__ void __launch_bounds__(512, 1) proj_fwd_ts_kernel(const __grid_consta
   const int d = P.d;
   const int stages = P.stages;
   const uint32_t b_bytes = (uint32_t)d * 128u;
-  const uint32_t stage_bytes = kTileA + 2u * b_bytes;           // A fp32 | W (-> W_hi in place) | W_lo
+  const uint32_t stage_bytes = kTileA + 2u * b_bytes;           // A fp32 | W_hi | W_lo
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
   uint64_t* full = bars; uint64_t* xform = bars + stages; uint64_t* empty = bars + 2 * stages;
   uint64_t* tfull = bars + 3 * stages; uint64_t* tempty = tfull + 2;
@@ -68,9 +67,10 @@ __global__ void __launch_bounds__(512, 1) proj_fwd_ts_kernel(const __grid_consta
       const int kb_n = P.prob[p].kblocks;
       for (int kb = 0; kb < kb_n; ++kb) {
         mbar_wait(&empty[st.stage], st.phase ^ 1);
-        mbar_arrive_expect_tx(&full[st.stage], kTileA + b_bytes);
+        mbar_arrive_expect_tx(&full[st.stage], stage_bytes);
         tma_load_2d(sA(st.stage), &P.tmA[p], &full[st.stage], kb * BK, mblk * BM);
-        tma_load_2d(sB(st.stage), &P.tmW[p], &full[st.stage], kb * BK, 0);       // fp32 W tile; split in smem by the transform warps
+        tma_load_2d(sB(st.stage), &P.tmW[p], &full[st.stage], kb * BK, 0);
+        tma_load_2d(sBlo(st.stage), &P.tmW[p], &full[st.stage], kb * BK, d);
         st.advance();
       }
     }
@@ -132,9 +132,6 @@ __global__ void __launch_bounds__(512, 1) proj_fwd_ts_kernel(const __grid_consta
         }
         tmem_st_32x32(lane_base + (uint32_t)(stage * kSlotCols), hi);
         tmem_st_32x32(lane_base + (uint32_t)(stage * kSlotCols + 32), lo);
-        // W tile -> W_hi (in place) + W_lo: halves the L2 -> SM traffic of the weights (they are re-read for every row tile)
-        split_tile_inplace(reinterpret_cast<float4*>(sB(stage)), reinterpret_cast<float4*>(sBlo(stage)), (int)(b_bytes / 16), row, 128);
-        fence_proxy_async_smem();
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&xform[stage]);
