@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(384, 1) proj_fwd_tc_kernel(const __grid_consta
     for (int p = 0; p < P.n_prob; ++p) { prefetch_tmap(&P.tmA[p]); prefetch_tmap(&P.tmW[p]); }
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&xform[s], 128); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&xform[s], 4);   /* one arrival per transform warp: 128 per-thread arrivals on one mbarrier serialise (~1000 clk per stage) */ mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
     fence_barrier_init();
   }
@@ -181,7 +181,8 @@ __global__ void __launch_bounds__(384, 1) proj_fwd_tc_kernel(const __grid_consta
         mbar_wait(&full[st.stage], st.phase);
         split_tile_inplace(reinterpret_cast<float4*>(sA(st.stage)), reinterpret_cast<float4*>(sAlo(st.stage)), kTileA / 16, tid, 128);
         fence_proxy_async_smem();
-        mbar_arrive(&xform[st.stage]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&xform[st.stage]);
         st.advance();
       }
     }
@@ -267,7 +268,7 @@ __global__ void __launch_bounds__(384, 1) proj_wgrad_tc_kernel(const __grid_cons
     for (int p = 0; p < P.n_prob; ++p) { prefetch_tmap(&P.tmX[p]); prefetch_tmap(&P.tmG[p]); }
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&xform[s], 128); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&xform[s], 4);   /* one arrival per transform warp: 128 per-thread arrivals on one mbarrier serialise (~1000 clk per stage) */ mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
     fence_barrier_init();
   }
@@ -349,7 +350,8 @@ __global__ void __launch_bounds__(384, 1) proj_wgrad_tc_kernel(const __grid_cons
         split_tile_inplace(reinterpret_cast<float4*>(sA(st.stage)), reinterpret_cast<float4*>(sAlo(st.stage)), kTileA / 16, tid, 128);
         split_tile_inplace(reinterpret_cast<float4*>(sB(st.stage)), reinterpret_cast<float4*>(sBlo(st.stage)), (int)(b_bytes / 16), tid, 128);
         fence_proxy_async_smem();
-        mbar_arrive(&xform[st.stage]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&xform[st.stage]);
         st.advance();
       }
     }

@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(512, 1) proj_fwd_ts_kernel(const __grid_consta
     for (int p = 0; p < P.n_prob; ++p) { prefetch_tmap(&P.tmA[p]); prefetch_tmap(&P.tmW[p]); }
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&xform[s], 128); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&xform[s], 4);   /* one arrival per transform warp: 128 per-thread arrivals on one mbarrier serialise (~1000 clk per stage) */ mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
     fence_barrier_init();
   }
@@ -134,7 +134,8 @@ __global__ void __launch_bounds__(512, 1) proj_fwd_ts_kernel(const __grid_consta
         tmem_st_32x32(lane_base + (uint32_t)(stage * kSlotCols + 32), lo);
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&xform[stage]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&xform[stage]);
       }
     }
   } else if (warp >= 8 && warp < 12) {
@@ -206,7 +207,7 @@ __global__ void __launch_bounds__(512, 1) proj_wgrad_ts_kernel(const __grid_cons
     for (int p = 0; p < P.n_prob; ++p) { prefetch_tmap(&P.tmX[p]); prefetch_tmap(&P.tmG[p]); }
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&xform[s], 128); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&xform[s], 4);   /* one arrival per transform warp: 128 per-thread arrivals on one mbarrier serialise (~1000 clk per stage) */ mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
     fence_barrier_init();
   }
@@ -301,7 +302,8 @@ __global__ void __launch_bounds__(512, 1) proj_wgrad_ts_kernel(const __grid_cons
         fence_proxy_async_smem();
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&xform[stage]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&xform[stage]);
       }
     }
   } else if (warp >= 8 && warp < 12) {

@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(384, 1) score_topk_tc_kernel(const __grid_cons
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
-    mbar_init(a_ready, 128);
+    mbar_init(a_ready, 4);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
@@ -139,7 +139,8 @@ __global__ void __launch_bounds__(384, 1) score_topk_tc_kernel(const __grid_cons
     }
     tmem_st_wait();
     tc_fence_before();
-    mbar_arrive(a_ready);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(a_ready);
   } else if (warp >= 8) {
     // ===== epilogue: fused masking + top-K' selection, one user row per thread =====
     const int wq = warp & 3;
