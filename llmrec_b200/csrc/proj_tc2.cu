@@ -13,6 +13,7 @@
 // Warp roles (512 threads): w0 TMA | w1 MMA | w2 TMEM alloc | w4-7 + w12-15 two transform groups alternating k-blocks |
 // w8-11 epilogue; barriers, tile scheduling and epilogues are those of proj_tc.cu.  Supports d <= 128 (TMEM: 2 accumulators of
 // d columns + 4 ring slots of 64 columns); larger d falls back to v1.
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 #include "proj_tc.cuh"
@@ -231,6 +232,7 @@ __global__ void __launch_bounds__(512, 1) proj_wgrad_ts_kernel(const __grid_cons
   };
 
   if (warp == 0 && lane == 0) {
+    // ===== TMA producer (issuing the six boxes of a stage from several lanes in parallel was measured: no gain) =====
     PipeState st(stages);
     for (int item = blockIdx.x; item < P.total_items; item += gridDim.x) {
       int p, ft, r0, kb_n; locate(item, p, ft, r0, kb_n);
