@@ -112,7 +112,6 @@ def step_bytes(tr):
 
 def run_ours(a):
     import torch
-    import torch.distributed as dist
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     if world > 1 or a.workload == "synthetic":
         from llmrec_b200.dist_bench import run_sharded

@@ -18,7 +18,6 @@ This is the ID-only configuration (no side-feature tables), the one the 10M x 1M
 """
 from __future__ import annotations
 
-import numpy as np
 import torch
 import torch.distributed as dist
 

@@ -148,7 +148,6 @@ def run_sharded(a):
         dist.barrier()
     if rank != 0:
         return None
-    import json
     from bench import peaks
     hbm, _, src = peaks()
     return {"metric": "train_interactions_per_sec", "value": round(B * K / (ms / 1e3), 1), "unit": "interactions/s", "n_gpus": world, "steps": K,

@@ -27,7 +27,6 @@ import numpy as np
 import scipy.sparse as sp
 import torch
 
-from . import ops
 from .Models import MM_Model
 from .graph import BipartiteGraph
 from .runtime import get_args, set_args

@@ -13,8 +13,6 @@ def _gen(tiny_root, sampler):
 
 
 def test_native_sampler_matches_reference_golden(tiny_root, golden):
-    import llmrec_b200.runtime as rt
-    from llmrec_b200.utility.parser import parse_args
     gen = _gen(tiny_root, "native")
     import pickle
     aug = pickle.load(open(os.path.join(tiny_root, "netflix_valid_item", "augmented_sample_dict"), "rb"))

@@ -1,6 +1,4 @@
 """Host-side SpMM tile planner (llmrec_spmm_plan_tiles): every row is covered exactly once, nnz bounds hold."""
-import ctypes
-
 import numpy as np
 
 from llmrec_b200 import _native as N
