@@ -110,9 +110,10 @@ class ShardedHotPath:
         self.Il = [E_i] + [new(ni, d) for _ in range(L)]
         self.U, self.I = new(nu, d), new(ni, d)
         self.part = new(ni, d)                       # per-rank partial of an item-side product (all-reduced in place)
-        self.gU, self.gI = new(nu, d), new(ni, d)
-        self.g_Eu, self.g_Ei = new(nu, d), new(ni, d)
-        self.dIl, self.bufU, self.bufI, self.tmpI = new(ni, d), new(nu, d), new(ni, d), new(ni, d)
+        self.parts = [self.part, new(ni, d)]         # backward chain ping-pong (the reduced partial IS the next gradient)
+        self.gU = new(nu, d)
+        self.g_Eu, self.g_Ei = new(nu, d), None
+        self.dIl, self.bufU, self.tmpI = new(ni, d), new(nu, d), new(ni, d)
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
         self.head_out = torch.zeros(4, dtype=torch.float32, device=dev)
         self._B = None
@@ -127,74 +128,90 @@ class ShardedHotPath:
             dist.all_reduce(t, group=self.group)
             self.comm_bytes += t.numel() * 4
 
-    def _exchange(self, which, src):
+    def _exchange(self, which, src, out=None):
         """self.part = sum over ranks of (item-side operator `which`) . src.  With item-row pieces, the NCCL all-reduce of
         piece k runs on NCCL's stream while the SpMM of piece k+1 runs on the compute stream (NVLink transfer hidden
         behind the gather)."""
         g = self.g
+        part = self.part if out is None else out
         if self.world == 1 or not g.pieces:
-            (g.iu_raw if which == "iu" else g.uiT_raw).apply([(src, self.part, None, False)])
-            self._allreduce(self.part)
+            (g.iu_raw if which == "iu" else g.uiT_raw).apply([(src, part, None, False)])
+            self._allreduce(part)
             return
         works = []
         for lo, hi, fwd, bwd in g.pieces:
-            (fwd if which == "iu" else bwd).apply([(src, self.part[lo:hi], None, False)])
-            works.append(dist.all_reduce(self.part[lo:hi], group=self.group, async_op=True))
+            (fwd if which == "iu" else bwd).apply([(src, part[lo:hi], None, False)])
+            works.append(dist.all_reduce(part[lo:hi], group=self.group, async_op=True))
             self.comm_bytes += (hi - lo) * self.d * 4
         for w in works:
             w.wait()
 
     # -- forward (Models.py:169-186) ------------------------------------------------------------------------
-    def forward(self):
+    def forward(self, fuse_items=True):
+        """fuse_items=False (training): the fused item output I is only needed on the batch's pos/neg rows and is
+        produced there by loss_and_output_grads -- the [ni x d] mean over layers is replicated work on every rank."""
         L = self.L
         for l in range(1, L + 1):
             self.g.ui.apply([(self.Il[l - 1], self.Ul[l], None, l == L)])                    # U_l = [softmax] ui . I_{l-1}
             self._exchange("iu", self.Ul[l])                                                  # sum_r R_r^T U_l  (all-reduce)
             ops.row_scale_softmax(self.part, self.g.si, self.Il[l], l == L)                   # I_l = [softmax] si (.) sum
         ops.fuse_fwd(self.Ul, [], [], self.U)                                                 # mean over layers (:185-186)
-        ops.fuse_fwd(self.Il, [], [], self.I)
+        if fuse_items:
+            ops.fuse_fwd(self.Il, [], [], self.I)
         return self.U, self.I
 
     # -- loss + output grads ------------------------------------------------------------------------------------
     def loss_and_output_grads(self, users, pos, neg):
-        """users: GLOBAL user ids (int32, identical on every rank); pos/neg: item ids."""
+        """users: GLOBAL user ids (int32, identical on every rank); pos/neg: item ids.
+        Item-side gradients of the loss are ROW-SPARSE (<= 2B' rows): they are kept compact ([2B' x d], indexed by batch
+        position) and scatter-added where the dense chain needs them, instead of carrying dense [ni x d] copies."""
         c = self.cfg
         B = int(users.numel())
         if self._B != B:
             dev = users.device
             self._B = B
             self.Ub, self.gUb = torch.empty(B, self.d, device=dev), torch.empty(B, self.d, device=dev)
+            self.Ib, self.gIb = torch.empty(2 * B, self.d, device=dev), torch.empty(2 * B, self.d, device=dev)
             self.arange = torch.arange(B, dtype=torch.int32, device=dev)
+            self.arange2 = self.arange + B
+            self.pn = torch.empty(2 * B, dtype=torch.int32, device=dev)
             self.work = ops.bpr_work(1, B, dev)
         local = owner_local_index(users, self.lo, self.hi)
         ops.gather_rows(self.U, local, self.Ub)                                               # owners fill, others zero
         self._allreduce(self.Ub)
-        self.loss.zero_(); self.gUb.zero_(); self.gI.zero_(); self.gU.zero_()
+        self.pn[:B].copy_(pos); self.pn[B:].copy_(neg)
+        ops.fuse_fwd(self.Il, [], [], self.I, rows=self.pn)                                   # I on the batch rows only
+        ops.gather_rows(self.I, self.pn, self.Ib)
+        self.loss.zero_(); self.gUb.zero_(); self.gIb.zero_(); self.gU.zero_()
         n_keep = int((1 - c.prune_loss_drop_rate) * B)
-        ops.bpr_heads([(self.Ub, self.I, self.gUb, self.gI, 1.0, 1.0)], self.arange, pos, neg, n_keep, c.regs0 / c.batch_size,
-                      self.head_out, self.loss, self.work)
+        ops.bpr_heads([(self.Ub, self.Ib, self.gUb, self.gIb, 1.0, 1.0)], self.arange, self.arange, self.arange2, n_keep,
+                      c.regs0 / c.batch_size, self.head_out, self.loss, self.work)
         ops.scatter_add_rows(self.gUb, local, self.gU)
+        self.gIb.mul_(1.0 / (self.L + 1))                                                     # rows of dIl = gI / (L+1)
         return self.loss
 
     # -- backward chain ---------------------------------------------------------------------------------------------
     def backward(self):
         L = self.L
         ops.fuse_bwd(self.gU, L + 1, self.g_Eu, [], [], [], True)                             # dUl (= grad of E_u) = gU/(L+1)
-        ops.fuse_bwd(self.gI, L + 1, self.dIl, [], [], [], True)
+        self.dIl.zero_()
+        ops.scatter_add_rows(self.gIb, self.pn, self.dIl)                                     # dense dIl only feeds the softmax bwd
         g_cur = self.dIl
+        grad_Ei = None
         for l in range(L, 0, -1):
             src = ops.row_softmax_bwd(self.Il[l], g_cur, out=self.tmpI) if l == L else g_cur
             self.g.iuT.apply([(src, self.bufU, self.g_Eu, False)])                            # gU_l = dUl + iu^T src   (local rows)
             if l == L:
                 ops.row_softmax_bwd(self.Ul[l], self.bufU, out=self.bufU)
-            self._exchange("uiT", self.bufU)                                                  # sum_r R_r^T (su (.) gU_l)
-            dst = self.g_Ei if l == 1 else self.bufI
-            torch.add(self.part, self.dIl, out=dst)                                           # gI_{l-1} = dIl + sum
-            g_cur = dst
+            self._exchange("uiT", self.bufU, out=self.parts[l & 1])                           # sum_r R_r^T (su (.) gU_l)
+            g_cur = self.parts[l & 1]
+            ops.scatter_add_rows(self.gIb, self.pn, g_cur)                                    # gI_{l-1} = sum + dIl (row-sparse addend)
+            grad_Ei = g_cur
+        self.g_Ei = grad_Ei
         return self.g_Eu, self.g_Ei
 
     def train_step(self, users, pos, neg):
-        self.forward()
+        self.forward(fuse_items=False)
         self.loss_and_output_grads(users, pos, neg)
         self.backward()
         self.opt.step([self.g_Eu, self.g_Ei])

@@ -47,7 +47,11 @@ def main():
         neg = torch.from_numpy(rng.integers(0, ni, 280).astype(np.int32)).to(dev)
         l1 = float(hp.train_step(users, pos, neg)); l2 = float(sh.train_step(users, pos, neg))
         ok &= abs(l1 - l2) < 1e-5 * max(1.0, abs(l1))
-        ok &= bool(torch.allclose(sh.U, hp.U[lo:hi], rtol=1e-4, atol=1e-6)) and bool(torch.allclose(sh.I, hp.I, rtol=1e-4, atol=1e-6))
+        ok &= bool(torch.allclose(sh.U, hp.U[lo:hi], rtol=1e-4, atol=1e-6))
+        rows = torch.cat([pos, neg]).long()           # the training step fuses I on the batch rows only
+        ok &= bool(torch.allclose(sh.I[rows], hp.I[rows], rtol=1e-4, atol=1e-6))
+    hp.forward(); sh.forward()                        # full forward (eval form)
+    ok &= bool(torch.allclose(sh.U, hp.U[lo:hi], rtol=1e-4, atol=1e-6)) and bool(torch.allclose(sh.I, hp.I, rtol=1e-4, atol=1e-6))
     ok &= bool(torch.allclose(sh.E_u, params["user_id_embedding.weight"][lo:hi], rtol=1e-4, atol=1e-6))
     ok &= bool(torch.allclose(sh.E_i, params["item_id_embedding.weight"], rtol=1e-4, atol=1e-6))
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)
