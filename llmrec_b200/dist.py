@@ -236,3 +236,23 @@ def synthetic_shard(n_users, n_items, n_edges, rank, world, device, seed=0, zipf
     items = perm[torch.searchsorted(cdf, torch.rand(users.numel(), device=device, generator=g)).clamp_(max=n_items - 1)]
     key = torch.unique(users * n_items + items)
     return key // n_items, key % n_items, lo, hi
+
+
+def store_shard(path, rank, world, device, split="train"):
+    """This rank's slice of a binary CSR interaction store (utility/csr_store.py): users [lo, hi) of the contiguous
+    partition, read straight from the memory-mapped arrays (only this rank's pages are touched).
+    -> (u_local int64, items int64, lo, hi, n_users, n_items); duplicate (user, item) pairs are removed, as scipy's
+    CSR construction of `train_mat` does upstream (main.py:59, 114-118 see a binary matrix)."""
+    from .utility import csr_store
+    import numpy as np
+    meta, rows = csr_store.read(path)
+    r = rows[split]
+    n_users, n_items = int(meta["n_users"]), int(meta["n_items"])
+    b = shard_bounds(n_users, world)
+    lo, hi = b[rank], b[rank + 1]
+    e0, e1 = int(r.rowptr[lo]), int(r.rowptr[hi])
+    counts = np.diff(np.asarray(r.rowptr[lo:hi + 1]))
+    u = torch.repeat_interleave(torch.arange(hi - lo, dtype=torch.int64), torch.from_numpy(counts.astype(np.int64)))
+    it = torch.from_numpy(np.asarray(r.col[e0:e1]).astype(np.int64))
+    key = torch.unique(u.to(device) * n_items + it.to(device))
+    return key // n_items, key % n_items, lo, hi, n_users, n_items

@@ -81,7 +81,12 @@ class Trainer(object):
         self.image_feats = np.load(os.path.join(ddir, "image_feat.npy"))                     # main.py:54-55
         self.text_feats = np.load(os.path.join(ddir, "text_feat.npy"))
         self.image_feat_dim, self.text_feat_dim = self.image_feats.shape[-1], self.text_feats.shape[-1]
-        self.ui_graph_raw = rd("train_mat")                                                  # :59
+        if os.path.exists(os.path.join(ddir, "train_mat")):
+            self.ui_graph_raw = rd("train_mat")                                              # :59
+        else:                                                                                # CSR store (utility/csr_store.py): same matrix, no pickle
+            rowptr, col = data_generator.csr("train")
+            self.ui_graph_raw = sp.csr_matrix((np.ones(col.shape[0], dtype=np.float32), col, rowptr),
+                                              shape=(data_generator.n_users, data_generator.n_items))
         self.user_init_embedding = _stack_rows(rd("augmented_user_init_embedding"))          # :61-67
         raw_att = rd("augmented_atttribute_embedding_dict")                                  # :69-79
         self.item_attribute_embedding = {k: _stack_rows(raw_att[k]) for k in raw_att}

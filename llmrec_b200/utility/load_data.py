@@ -11,6 +11,9 @@ test_set / val_set / R and `sample()`.  Differences from the reference, all beha
     (load_data.py:157-195), so seeded runs draw identical batches.  `sampler="native"` runs the same
     algorithm in C (llmrec_b200/csrc/host_sampler.c): MT19937 + numpy's legacy masked-rejection
     bounded integers, state handed over with np.random.get_state()/set_state() -- bit-identical.
+  * when the directory holds the binary CSR form of the three json files (utility/csr_store.py)
+    it is memory-mapped instead of parsed: same attributes, `train_items / test_set / val_set` are read-only
+    mappings over the arrays, no per-interaction Python work (the json walk is minutes at 200 M edges).
 """
 import json
 import os
@@ -18,6 +21,8 @@ import random as rd
 
 import numpy as np
 import scipy.sparse as sp
+
+from . import csr_store
 
 
 def _csr_from_dict(d, n_rows):
@@ -37,6 +42,13 @@ class Data(object):
         self.n_users = self.n_items = self.n_train = self.n_test = 0
         self.neg_pools = {}
         self.exist_users = []
+        self._R = None
+        self._csr = {}
+        self._sampler = sampler
+        self._native = None
+        if csr_store.present(path):
+            self._init_from_csr(path)
+            return
 
         def load(name):
             with open(os.path.join(path, name + ".json")) as f:
@@ -69,10 +81,23 @@ class Data(object):
         text = np.load(os.path.join(path, "text_feat.npy"), mmap_mode="r")
         self.n_items = int(text.shape[0])                      # :57-58 overrides the json maximum
         self.print_statistics()
-        self._R = None
-        self._csr = {}
-        self._sampler = sampler
-        self._native = None
+
+    def _init_from_csr(self, path):
+        meta, rows = csr_store.read(path)
+        if "train" not in rows:
+            raise ValueError("%s: the CSR store has no train split" % path)
+        empty = csr_store.CsrRows(np.zeros(meta["n_users"] + 1, dtype=np.int64), np.zeros(0, dtype=np.int32))
+        self.train_items = rows["train"]
+        self.test_set, self.val_set = rows.get("test", empty), rows.get("val", empty)
+        self.exist_users = self.train_items.order().tolist()
+        self.n_users = int(meta["n_users"])                    # = max train uid + 1 (csr_store.convert_json)
+        self.n_train = int(self.train_items.col.shape[0])
+        self.n_test = int(self.test_set.col.shape[0])
+        text = os.path.join(path, "text_feat.npy")
+        self.n_items = int(np.load(text, mmap_mode="r").shape[0]) if os.path.exists(text) else int(meta["n_items"])
+        for which, r in (("train", self.train_items), ("test", self.test_set), ("val", self.val_set)):
+            self._csr[which] = (np.asarray(r.rowptr, dtype=np.int32), np.asarray(r.col, dtype=np.int32))
+        self.print_statistics()
 
     # -- matrices ---------------------------------------------------------------------------------
     def csr(self, which="train", sorted_rows=False):
