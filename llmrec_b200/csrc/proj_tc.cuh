@@ -15,7 +15,7 @@ struct FwdParams {
   CUtensorMap tmA[kMaxProb];
   CUtensorMap tmW[kMaxProb];  // [2d x k] (hi rows then lo rows) when SPLIT, [d x k] otherwise
   FwdProblem prob[kMaxProb];
-  int n_prob, total_tiles, d, stages, tmem_cols, dbg;
+  int n_prob, total_tiles, d, stages, tmem_cols;
 };
 
 
@@ -24,7 +24,7 @@ struct WgParams {
   CUtensorMap tmX[kMaxProb];
   CUtensorMap tmG[kMaxProb];
   WgProblem prob[kMaxProb];
-  int n_prob, total_items, d, stages, tmem_cols, dbg;
+  int n_prob, total_items, d, stages, tmem_cols;
   float* partial;  // [total_items][128][d]
 };
 

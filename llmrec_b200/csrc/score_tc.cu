@@ -35,7 +35,7 @@ struct ScoreParams {
   const float* U; long long ldu;
   const int* users; int n_batch, n_items, d;
   const int* mask_rowptr; const int* mask_col;  // train rows, columns sorted ascending
-  int Kc, splits, tiles_per_split, stages, tmem_cols, debug;
+  int Kc, splits, tiles_per_split, stages, tmem_cols;
   int* cand_idx; float* cand_val;  // [n_batch][splits][Kc]
 };
 
@@ -210,12 +210,11 @@ __global__ void __launch_bounds__(384, 1) score_topk_tc_kernel(const __grid_cons
         uint32_t r[32];
         tmem_ld_32x32(t0 + c0, r);
         tmem_ld_wait();
-        if (P.debug == 1) continue;   // profiling aid: pipeline without the selection
         // fast path: one compare per score builds the mask of columns that beat the current threshold
         unsigned hit = 0;
 #pragma unroll
         for (int j = 0; j < 32; ++j) hit |= (__uint_as_float(r[j]) > thr ? 1u : 0u) << j;
-        if (!live || P.debug == 2) hit = 0;
+        if (!live) hit = 0;
         const int item0 = t * SBN + c0;
         if (hit) {
           // slow path: park the 32 scores in this thread's scratch column and walk the set bits in ascending item id with
@@ -358,7 +357,6 @@ int score_topk_tc(const float* U, long long ldu, const float* I, long long ldi, 
   P.U = U; P.ldu = ldu; P.users = users; P.n_batch = n_batch; P.n_items = n_items; P.d = d;
   P.mask_rowptr = mask_rowptr; P.mask_col = mask_col; P.cand_idx = cidx; P.cand_val = cval;
   P.tmem_cols = 512;
-  P.debug = getenv("LLMREC_SCORE_DEBUG") ? atoi(getenv("LLMREC_SCORE_DEBUG")) : 0;
   const size_t list_bytes = (size_t)P.Kc * SBM * 8 + 32 * SBM * 4;
   int stages = (int)((225 * 1024 - list_bytes - 512) / (2 * 16384));
   if (stages > 6) stages = 6;
