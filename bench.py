@@ -125,7 +125,7 @@ def run_ours(a):
     ds, nu, ni, ne, dims, embed, wsize = WORKLOADS[a.workload]
     root = ensure_dataset(a.workload)
     args = set_args(parse_args(["--data_path", root, "--dataset", ds, "--debug", "--epoch", "1", "--embed_size", str(embed),
-                                "--weight_size", wsize, "--proj_mode", a.proj_mode, "--host_sampler", a.host_sampler, "--cuda_graph", str(a.graph)]))
+                                "--weight_size", wsize, "--proj_mode", a.proj_mode, "--feat_layout", a.feat_layout, "--host_sampler", a.host_sampler, "--cuda_graph", str(a.graph)]))
     torch.cuda.set_device(0)
     M.set_seed(args.seed)
     import contextlib
@@ -228,7 +228,7 @@ def run_ours(a):
            "data": "synthetic", "impl": "ours",
            "config": {"workload": f"{a.workload}-shaped synthetic {nu}x{ni}, {gen.n_train} train edges, d={embed}, L={len(eval(wsize))}, batch=1024 (+aug edges), feature dims {list(dims)}",
                       "interactions_counted": "sum(len(users)) incl. augmented edges", "l2": "inputs larger than L2 (704 MB of features per step)",
-                      "proj_mode": a.proj_mode, "host_sampler": a.host_sampler, "cuda_graph": bool(a.graph)},
+                      "proj_mode": a.proj_mode, "feat_layout": a.feat_layout, "host_sampler": a.host_sampler, "cuda_graph": bool(a.graph)},
            "e2e": {"value": round(n_e2e / (ms_e2e / 1e3), 1), "unit": "interactions/s", "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": 4,
                    "ms_per_step": round(ms_e2e / K, 4)},
            "gpu_launches": launches, "clocks": clk, "roofline": roof, "eval": ev}
@@ -305,6 +305,7 @@ def main():
     ap.add_argument("--eval-users", dest="eval_users", type=int, default=102400, help="users ranked in the synthetic eval leg")
     ap.add_argument("--syn-scale", dest="syn_scale", type=float, default=1.0, help="size factor of the 10M x 1M x 200M synthetic graph")
     ap.add_argument("--proj_mode", default="3xtf32")
+    ap.add_argument("--feat_layout", default="rows", choices=["rows", "panels"])
     ap.add_argument("--host_sampler", default="native")
     ap.add_argument("--no-cpu", dest="no_cpu", action="store_true")
     ap.add_argument("--graph", type=int, default=1)

@@ -106,7 +106,8 @@ class MM_Model(nn.Module):
                                 user_cat_rate=args.user_cat_rate, item_cat_rate=args.item_cat_rate, aug_mf_rate=args.aug_mf_rate,
                                 mm_mf_rate=args.mm_mf_rate, prune_loss_drop_rate=args.prune_loss_drop_rate,
                                 feat_reg_decay=args.feat_reg_decay, regs0=eval(args.regs)[0], batch_size=args.batch_size,
-                                proj_mode=PROJ_MODE[getattr(args, "proj_mode", "3xtf32")])
+                                proj_mode=PROJ_MODE[getattr(args, "proj_mode", "3xtf32")],
+                                feat_layout=1 if getattr(args, "feat_layout", "rows") == "panels" else 0)
             self._hp = HotPath((ui_f, iu_f, ui_b, iu_b), params, feats, cfg)
             self._hp_key = key
         return self._hp

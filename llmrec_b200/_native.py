@@ -30,7 +30,7 @@ class SpmmTiling(C.Structure):
 
 class ProjFwdProblem(C.Structure):
     _fields_ = [("X", C.c_void_p), ("W", C.c_void_p), ("bias", C.c_void_p), ("Y", C.c_void_p), ("wsplit", C.c_void_p),
-                ("ldx", C.c_int64), ("ldy", C.c_int64), ("n", C.c_int64), ("k", C.c_int32), ("_pad", C.c_int32)]
+                ("ldx", C.c_int64), ("ldy", C.c_int64), ("n", C.c_int64), ("k", C.c_int32), ("x_layout", C.c_int32)]
 
 
 class ProjWgradProblem(C.Structure):
@@ -84,6 +84,7 @@ SIGNATURES = {
     "llmrec_gather_rows_f32": (C.c_int, [c_f32p, C.c_int64, c_i32p, C.c_int32, C.c_int32, c_f32p, C.c_int64, c_stream]),
     "llmrec_scatter_add_rows_f32": (C.c_int, [c_f32p, C.c_int64, c_i32p, C.c_int32, C.c_int32, c_f32p, C.c_int64, c_stream]),
     "llmrec_fill_f32": (C.c_int, [c_f32p, C.c_int64, C.c_float, c_stream]),
+    "llmrec_panelize_f32": (C.c_int, [c_f32p, C.c_int64, C.c_int64, C.c_int32, c_f32p, c_stream]),
 }
 
 _lib = None

@@ -127,7 +127,9 @@ __global__ void __launch_bounds__(384, 1) proj_fwd_tc_kernel(const __grid_consta
       for (int kb = 0; kb < kb_n; ++kb) {
         mbar_wait(&empty[st.stage], st.phase ^ 1);
         mbar_arrive_expect_tx(&full[st.stage], kTileA + b_bytes * (SPLIT ? 2u : 1u));
-        tma_load_2d(sA(st.stage), &P.tmA[p], &full[st.stage], kb * BK, mblk * BM);
+        // panels: tile (panel kb, rows mblk*BM..) is one contiguous 16 KiB run; rows past n read the next panel (finite, never stored)
+        if (P.prob[p].panel) tma_load_2d(sA(st.stage), &P.tmA[p], &full[st.stage], 0, kb * P.prob[p].n + mblk * BM);
+        else tma_load_2d(sA(st.stage), &P.tmA[p], &full[st.stage], kb * BK, mblk * BM);
         tma_load_2d(sB(st.stage), &P.tmW[p], &full[st.stage], kb * BK, 0);
         if (SPLIT) tma_load_2d(sBlo(st.stage), &P.tmW[p], &full[st.stage], kb * BK, d);
         st.advance();
@@ -300,7 +302,11 @@ __global__ void __launch_bounds__(384, 1) proj_wgrad_tc_kernel(const __grid_cons
         mbar_arrive_expect_tx(&full[st.stage], kTileA + b_bytes);
         const int r = r0 + kb * BK;
 #pragma unroll
-        for (int a = 0; a < 4; ++a) tma_load_2d(sA(st.stage) + a * 4096, &P.tmX[p], &full[st.stage], ft * BM + a * 32, r);
+        for (int a = 0; a < 4; ++a) {
+          // panels: rows past n read the next panel, where dY's box is zero-filled -> they add exactly 0
+          if (P.prob[p].panel) tma_load_2d(sA(st.stage) + a * 4096, &P.tmX[p], &full[st.stage], 0, (ft * 4 + a) * P.prob[p].n + r);
+          else tma_load_2d(sA(st.stage) + a * 4096, &P.tmX[p], &full[st.stage], ft * BM + a * 32, r);
+        }
         for (int b = 0; b < d / 32; ++b) tma_load_2d(sB(st.stage) + b * 4096, &P.tmG[p], &full[st.stage], b * 32, r);
         st.advance();
       }
@@ -503,7 +509,12 @@ int proj_fwd_tc_group(const llmrec_proj_fwd_problem* pr, int n_prob, int d, int 
       wsplit_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pr[p].W, pr[p].wsplit, n);
       LLMREC_CHECK_LAUNCH("wsplit");
     }
-    if (!make_tmap_2d_f32(&P.tmA[p], pr[p].X, (uint64_t)pr[p].k, (uint64_t)pr[p].n, (uint64_t)pr[p].ldx * 4, BK, BM)) return 4;
+    const bool panel = pr[p].x_layout == LLMREC_X_PANELS;
+    if (panel) {
+      LLMREC_CHECK_ARG(pr[p].k % BK == 0 && (int64_t)(pr[p].k / BK) * pr[p].n < (int64_t)INT32_MAX, "proj_fwd: panel layout needs k %% 32 == 0 and (k/32)*n < 2^31");
+      if (!make_tmap_2d_f32(&P.tmA[p], pr[p].X, (uint64_t)BK, (uint64_t)(pr[p].k / BK) * (uint64_t)pr[p].n, (uint64_t)BK * 4, BK, BM)) return 4;
+    } else if (!make_tmap_2d_f32(&P.tmA[p], pr[p].X, (uint64_t)pr[p].k, (uint64_t)pr[p].n, (uint64_t)pr[p].ldx * 4, BK, BM)) return 4;
+    P.prob[p].panel = panel ? 1 : 0;
     if (!make_tmap_2d_f32(&P.tmW[p], wsrc, (uint64_t)pr[p].k, (uint64_t)(split ? 2 * d : d), (uint64_t)pr[p].k * 4, BK, (uint32_t)d)) return 4;
     P.prob[p].n = (int)pr[p].n; P.prob[p].k = pr[p].k; P.prob[p].kblocks = (pr[p].k + BK - 1) / BK;
     P.prob[p].tile_start = tiles; P.prob[p].ldy = pr[p].ldy; P.prob[p].Y = pr[p].Y; P.prob[p].bias = pr[p].bias;
@@ -553,15 +564,20 @@ int proj_wgrad_tc_group(const llmrec_proj_wgrad_problem* pr, int n_prob, int d, 
   memset(&C, 0, sizeof(C));
   C.d = d;
   for (int p = 0; p < n_prob; ++p) {
-    if (!make_tmap_2d_f32(&P.tmX[p], pr[p].X, (uint64_t)pr[p].k, (uint64_t)pr[p].n, (uint64_t)pr[p].ldx * 4, 32, BK, true)) return 4;
+    const bool panel = (pr[p].accumulate & LLMREC_WGRAD_X_PANELS) != 0;
+    if (panel) {
+      LLMREC_CHECK_ARG(pr[p].k % BK == 0 && (int64_t)(pr[p].k / BK + 4) * pr[p].n < (int64_t)INT32_MAX, "proj_wgrad: panel layout needs k %% 32 == 0 and (k/32 + 4)*n < 2^31");
+      if (!make_tmap_2d_f32(&P.tmX[p], pr[p].X, (uint64_t)32, (uint64_t)(pr[p].k / 32) * (uint64_t)pr[p].n, (uint64_t)128, 32, BK, true)) return 4;
+    } else if (!make_tmap_2d_f32(&P.tmX[p], pr[p].X, (uint64_t)pr[p].k, (uint64_t)pr[p].n, (uint64_t)pr[p].ldx * 4, 32, BK, true)) return 4;
     if (!make_tmap_2d_f32(&P.tmG[p], pr[p].dY, (uint64_t)d, (uint64_t)pr[p].n, (uint64_t)pr[p].lddy * 4, 32, BK, true)) return 4;
     WgProblem& w = P.prob[p];
     w.n = (int)pr[p].n; w.k = pr[p].k; w.ft_tiles = (pr[p].k + BM - 1) / BM;
     w.rows_per_chunk = wg_rows_per_chunk(pr[p].n);
     w.chunks = (int)((pr[p].n + w.rows_per_chunk - 1) / w.rows_per_chunk);
     w.item_start = items;
+    w.panel = panel ? 1 : 0;
     items += w.ft_tiles * w.chunks;
-    C.dY[p] = pr[p].dY; C.ld[p] = pr[p].lddy; C.n[p] = pr[p].n; C.db[p] = pr[p].db; C.acc[p] = pr[p].accumulate;
+    C.dY[p] = pr[p].dY; C.ld[p] = pr[p].lddy; C.n[p] = pr[p].n; C.db[p] = pr[p].db; C.acc[p] = pr[p].accumulate & LLMREC_WGRAD_ACCUMULATE;
   }
   P.total_items = items;
   const int64_t need = (int64_t)items * BM * d + (int64_t)n_prob * kColsumSlices * d;
@@ -595,7 +611,7 @@ int proj_wgrad_tc_group(const llmrec_proj_wgrad_problem* pr, int n_prob, int d, 
     for (int q = 0; q < R.n_out; ++q) if (R.out[q].dW == pr[p].dW) o = q;
     if (o < 0) {
       o = R.n_out++;
-      R.out[o].dW = pr[p].dW; R.out[o].k = pr[p].k; R.out[o].accumulate = pr[p].accumulate; R.out[o].n_src = 0;
+      R.out[o].dW = pr[p].dW; R.out[o].k = pr[p].k; R.out[o].accumulate = pr[p].accumulate & LLMREC_WGRAD_ACCUMULATE; R.out[o].n_src = 0;
     }
     LLMREC_CHECK_ARG(R.out[o].k == pr[p].k, "proj_wgrad: problems sharing dW must share k");
     R.out[o].src[R.out[o].n_src++] = p;

@@ -38,6 +38,7 @@ class HotPathConfig:
     regs0: float = 1e-5
     batch_size: int = 1024
     proj_mode: int = 0                # ops.PROJ_MODE
+    feat_layout: int = 0              # 0 = row-major feature tables, 1 = 32-column panels (ops.PanelFeat; tcgen05 modes only)
 
 
 PARAM_ORDER = ("image_trans.weight", "image_trans.bias", "text_trans.weight", "text_trans.bias",
@@ -86,6 +87,11 @@ class HotPath:
         self.has_feats = feats is not None
         self.keys = list(feats["item"].keys()) if self.has_feats else []
         S = self.S = (2 + len(self.keys)) if self.has_feats else 0
+        self.fx = feats                                                    # what the projection kernels read
+        if self.has_feats and cfg.feat_layout == 1 and cfg.proj_mode != 2:
+            pf = lambda t: ops.PanelFeat(t) if t.shape[1] % 32 == 0 else t
+            self.fx = dict(image=pf(feats["image"]), text=pf(feats["text"]), user=pf(feats["user"]),
+                           item={k: pf(v) for k, v in feats["item"].items()})
         if self.has_feats:
             self.Pi, self.Fu, self.Fi = new(ni, S * d), new(nu, S * d), new(ni, S * d)
             self.P_usr, self.prof_i, self.prof_u = new(nu, d), new(ni, d), new(nu, d)
@@ -135,7 +141,7 @@ class HotPath:
 
     def _proj_fwd(self):
         d, m = self.d, self.cfg.proj_mode
-        p, f = self.p, self.feats
+        p, f = self.p, self.fx
         if self.has_feats:
             with self._t("proj_fwd"):                                                                                # Models.py:145-150
                 probs = [(f["image"], p["image_trans.weight"], p["image_trans.bias"], self.blk(self.Pi, 0)),
@@ -240,7 +246,7 @@ class HotPath:
     def _wgrad(self):
         d, m = self.d, self.cfg.proj_mode
         if self.has_feats:
-            f, g = self.feats, self.grads
+            f, g = self.fx, self.grads
             with self._t("proj_wgrad"):
                 probs = [(f["item"][k], self.blk(self.GPi, 2 + j), g["item_trans.weight"], g["item_trans.bias"], j > 0) for j, k in enumerate(self.keys)]
                 probs.append((f["user"], self.GP_usr, g["user_trans.weight"], g["user_trans.bias"], False))
