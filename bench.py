@@ -301,6 +301,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="netflix", choices=list(WORKLOADS) + ["synthetic"])
     ap.add_argument("--pieces", type=int, default=1, help="N>1: item-row pieces of the exchange SpMMs (all-reduce of piece k overlaps SpMM of piece k+1)")
+    ap.add_argument("--item-sharded", dest="item_sharded", type=int, default=0, help="N>1: reduce-scatter / row-local work / all-gather form of the item-side exchanges, AdamW of the item table sharded by item")
     ap.add_argument("--n1-base", dest="n1_base", type=int, default=1, help="N>1: also time the same synthetic workload on rank 0 alone")
     ap.add_argument("--eval-users", dest="eval_users", type=int, default=102400, help="users ranked in the synthetic eval leg")
     ap.add_argument("--syn-scale", dest="syn_scale", type=float, default=1.0, help="size factor of the 10M x 1M x 200M synthetic graph")

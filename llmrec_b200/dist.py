@@ -97,9 +97,15 @@ class ShardedGraph:
 class ShardedHotPath:
     """ID-only training step over a ShardedGraph; world size 1 reproduces engine.HotPath(feats=None) exactly."""
 
-    def __init__(self, graph: ShardedGraph, E_u_local: torch.Tensor, E_i: torch.Tensor, cfg: HotPathConfig, user_lo: int, group=None, solo=False):
+    def __init__(self, graph: ShardedGraph, E_u_local: torch.Tensor, E_i: torch.Tensor, cfg: HotPathConfig, user_lo: int, group=None, solo=False,
+                 item_sharded: bool = False):
+        """item_sharded (opt-in, needs n_items % world == 0): the item-side exchanges whose result is only consumed row-wise
+        become reduce-scatter -> row-local work on this rank's item range -> all-gather (same bytes on NVLink as the
+        all-reduce): the scale/softmax after each forward exchange runs on 1/world of the rows, and the item table's AdamW
+        state and update are sharded by item (the updated rows are all-gathered instead of the gradient)."""
         self.g, self.cfg, self.group = graph, cfg, group
         self.world = dist.get_world_size(group) if (dist.is_initialized() and not solo) else 1
+        self.item_sharded = bool(item_sharded) and self.world > 1 and E_i.shape[0] % self.world == 0
         self.E_u, self.E_i = E_u_local, E_i
         self.lo, self.hi = int(user_lo), int(user_lo) + E_u_local.shape[0]
         nu, ni, d, L = E_u_local.shape[0], E_i.shape[0], cfg.embed_size, cfg.n_layers
@@ -117,7 +123,14 @@ class ShardedHotPath:
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
         self.head_out = torch.zeros(4, dtype=torch.float32, device=dev)
         self._B = None
-        self.opt = ops.AdamW([E_u_local, E_i], lr=1e-4)
+        if self.item_sharded:
+            rank = dist.get_rank(group)
+            per = ni // self.world
+            self.ilo, self.ihi = rank * per, (rank + 1) * per
+            self.shard = new(per, d)                                       # this rank's rows of a reduced item-side product
+            self.opt = ops.AdamW([E_u_local, E_i[self.ilo:self.ihi]], lr=1e-4)
+        else:
+            self.opt = ops.AdamW([E_u_local, E_i], lr=1e-4)
         self.comm_bytes = 0
 
     def set_lr(self, lr):
@@ -127,6 +140,16 @@ class ShardedHotPath:
         if self.world > 1:
             dist.all_reduce(t, group=self.group)
             self.comm_bytes += t.numel() * 4
+
+    def _reduce_scatter(self, part):
+        """self.shard = this rank's item rows of sum over ranks of `part` ([ni x d], equal contiguous row ranges)."""
+        dist.reduce_scatter_tensor(self.shard, part, group=self.group)
+        self.comm_bytes += part.numel() * 2                                 # accounted like half an all-reduce
+
+    def _all_gather_rows(self, full):
+        """every rank's [ilo, ihi) rows of `full` -> all rows, in place."""
+        dist.all_gather_into_tensor(full, full[self.ilo:self.ihi], group=self.group)
+        self.comm_bytes += full.numel() * 2
 
     def _exchange(self, which, src, out=None):
         """self.part = sum over ranks of (item-side operator `which`) . src.  With item-row pieces, the NCCL all-reduce of
@@ -153,6 +176,12 @@ class ShardedHotPath:
         L = self.L
         for l in range(1, L + 1):
             self.g.ui.apply([(self.Il[l - 1], self.Ul[l], None, l == L)])                    # U_l = [softmax] ui . I_{l-1}
+            if self.item_sharded:
+                self.g.iu_raw.apply([(self.Ul[l], self.part, None, False)])                   # per-rank partial of R^T U_l
+                self._reduce_scatter(self.part)
+                ops.row_scale_softmax(self.shard, self.g.si[self.ilo:self.ihi], self.Il[l][self.ilo:self.ihi], l == L)
+                self._all_gather_rows(self.Il[l])
+                continue
             self._exchange("iu", self.Ul[l])                                                  # sum_r R_r^T U_l  (all-reduce)
             ops.row_scale_softmax(self.part, self.g.si, self.Il[l], l == L)                   # I_l = [softmax] si (.) sum
         ops.fuse_fwd(self.Ul, [], [], self.U)                                                 # mean over layers (:185-186)
@@ -203,6 +232,15 @@ class ShardedHotPath:
             self.g.iuT.apply([(src, self.bufU, self.g_Eu, False)])                            # gU_l = dUl + iu^T src   (local rows)
             if l == L:
                 ops.row_softmax_bwd(self.Ul[l], self.bufU, out=self.bufU)
+            if l == 1 and self.item_sharded:
+                # the last exchange yields the gradient of E_i, which only its (sharded) AdamW update reads
+                self.g.uiT_raw.apply([(self.bufU, self.part, None, False)])
+                self._reduce_scatter(self.part)
+                pn = self.pn.to(torch.int64)
+                own = (pn >= self.ilo) & (pn < self.ihi)
+                ops.scatter_add_rows(self.gIb, torch.where(own, pn - self.ilo, torch.full_like(pn, -1)).to(torch.int32), self.shard)
+                grad_Ei = self.shard
+                break
             self._exchange("uiT", self.bufU, out=self.parts[l & 1])                           # sum_r R_r^T (su (.) gU_l)
             g_cur = self.parts[l & 1]
             ops.scatter_add_rows(self.gIb, self.pn, g_cur)                                    # gI_{l-1} = sum + dIl (row-sparse addend)
@@ -215,6 +253,8 @@ class ShardedHotPath:
         self.loss_and_output_grads(users, pos, neg)
         self.backward()
         self.opt.step([self.g_Eu, self.g_Ei])
+        if self.item_sharded:
+            self._all_gather_rows(self.E_i)                                                   # updated item rows back to every rank
         return self.loss
 
 

@@ -34,7 +34,7 @@ def run_sharded(a):
     E_u = (torch.rand(hi - lo, d, device=dev, generator=torch.Generator(device=dev).manual_seed(77 + rank)) * 2 - 1) * bound
     E_i = (torch.rand(ni, d, device=dev, generator=gen) * 2 - 1) * (6.0 / (ni + d)) ** 0.5   # same seed on every rank: replicated
     cfg = HotPathConfig(embed_size=d, n_layers=L, batch_size=1024)
-    hp = ShardedHotPath(g, E_u, E_i, cfg, lo)
+    hp = ShardedHotPath(g, E_u, E_i, cfg, lo, item_sharded=bool(getattr(a, "item_sharded", 0)))
     nnz = torch.tensor([g.nnz], device=dev, dtype=torch.int64)
     if world > 1:
         dist.all_reduce(nnz)
@@ -155,7 +155,7 @@ def run_sharded(a):
             "data": "synthetic", "impl": "ours",
             "config": {"workload": f"synthetic {nu}x{ni}, {int(nnz)} unique edges (Zipf 0.8 item popularity), d={d}, L={L}, global batch {B} triplets, "
                                    "ID propagation + BPR/prune + dense AdamW, no side features; users sharded over ranks, items replicated",
-                       "l2": "inputs larger than L2", "graph_build_s": round(build_s, 1), "allreduce_bytes_per_step": comm_per_step,
+                       "l2": "inputs larger than L2", "graph_build_s": round(build_s, 1), "allreduce_bytes_per_step": comm_per_step, "item_sharded": bool(hp.item_sharded),
                        "cuda_graph": False},
             "e2e": {"value": round(B * K / (ms2 / 1e3), 1), "unit": "interactions/s", "h2d_bytes_per_step": 3 * 4 * B, "d2h_bytes_per_step": 4,
                     "ms_per_step": round(ms2 / K, 4)},

@@ -33,7 +33,7 @@ def main():
     lo, hi = b[rank], b[rank + 1]
     mine = e[(e[:, 0] >= lo) & (e[:, 0] < hi)]
     g = ShardedGraph(torch.from_numpy(mine[:, 0] - lo).to(dev), torch.from_numpy(mine[:, 1]).to(dev), hi - lo, ni, tile_nnz=32, pieces=(2 if world > 1 else 1))
-    sh = ShardedHotPath(g, Eu[lo:hi].clone().to(dev), Ei.clone().to(dev), cfg, lo)
+    sh = ShardedHotPath(g, Eu[lo:hi].clone().to(dev), Ei.clone().to(dev), cfg, lo, item_sharded=os.environ.get("LLMREC_DIST_ITEM_SHARDED") == "1")
     # reference: single-GPU engine on the full graph (every rank builds it; small)
     R = sp.csr_matrix((np.ones(len(e), np.float32), (e[:, 0], e[:, 1])), shape=(nu, ni))
     bg = BipartiteGraph(R, dev, tile_nnz=32)

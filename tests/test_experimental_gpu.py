@@ -78,3 +78,16 @@ def test_training_with_panel_features_is_identical(tiny_root):
         losses.append((ls, tr.model_mm.state_dict()["image_trans.weight"].clone()))
     assert losses[0][0] == losses[1][0]
     assert torch.equal(losses[0][1], losses[1][1])
+
+
+def test_item_sharded_exchange_world2_equals_engine():
+    """dist.ShardedHotPath(item_sharded=True): reduce-scatter / row-local / all-gather form == single-GPU engine."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, LLMREC_DIST_ITEM_SHARDED="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29519", os.path.join(here, "dist_gpu_check.py")], capture_output=True, text=True, timeout=600, env=env)
+    assert "DIST_CHECK_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
