@@ -127,8 +127,8 @@ __global__ void __launch_bounds__(384, 1) proj_fwd_tc_kernel(const __grid_consta
       for (int kb = 0; kb < kb_n; ++kb) {
         mbar_wait(&empty[st.stage], st.phase ^ 1);
         mbar_arrive_expect_tx(&full[st.stage], kTileA + b_bytes * (SPLIT ? 2u : 1u));
-        // panels: tile (panel kb, rows mblk*BM..) is one contiguous 16 KiB run; rows past n read the next panel (finite, never stored)
-        if (P.prob[p].panel) tma_load_2d(sA(st.stage), &P.tmA[p], &full[st.stage], 0, kb * P.prob[p].n + mblk * BM);
+        // panels: tile (panel kb, rows mblk*BM..) is one contiguous 16 KiB run (panels are zero-padded to a multiple of 128 rows)
+        if (P.prob[p].panel) tma_load_2d(sA(st.stage), &P.tmA[p], &full[st.stage], 0, kb * P.prob[p].panel + mblk * BM);
         else tma_load_2d(sA(st.stage), &P.tmA[p], &full[st.stage], kb * BK, mblk * BM);
         tma_load_2d(sB(st.stage), &P.tmW[p], &full[st.stage], kb * BK, 0);
         if (SPLIT) tma_load_2d(sBlo(st.stage), &P.tmW[p], &full[st.stage], kb * BK, d);
@@ -303,8 +303,8 @@ __global__ void __launch_bounds__(384, 1) proj_wgrad_tc_kernel(const __grid_cons
         const int r = r0 + kb * BK;
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
-          // panels: rows past n read the next panel, where dY's box is zero-filled -> they add exactly 0
-          if (P.prob[p].panel) tma_load_2d(sA(st.stage) + a * 4096, &P.tmX[p], &full[st.stage], 0, (ft * 4 + a) * P.prob[p].n + r);
+          // panels: one contiguous 4 KiB run per box; rows past n are the panel's zero padding, panels past k/32 are out of bounds (zero fill)
+          if (P.prob[p].panel) tma_load_2d(sA(st.stage) + a * 4096, &P.tmX[p], &full[st.stage], 0, (ft * 4 + a) * P.prob[p].panel + r);
           else tma_load_2d(sA(st.stage) + a * 4096, &P.tmX[p], &full[st.stage], ft * BM + a * 32, r);
         }
         for (int b = 0; b < d / 32; ++b) tma_load_2d(sB(st.stage) + b * 4096, &P.tmG[p], &full[st.stage], b * 32, r);
@@ -510,11 +510,12 @@ int proj_fwd_tc_group(const llmrec_proj_fwd_problem* pr, int n_prob, int d, int 
       LLMREC_CHECK_LAUNCH("wsplit");
     }
     const bool panel = pr[p].x_layout == LLMREC_X_PANELS;
+    const int64_t npad = LLMREC_PANEL_ROWS(pr[p].n);
     if (panel) {
-      LLMREC_CHECK_ARG(pr[p].k % BK == 0 && (int64_t)(pr[p].k / BK) * pr[p].n < (int64_t)INT32_MAX, "proj_fwd: panel layout needs k %% 32 == 0 and (k/32)*n < 2^31");
-      if (!make_tmap_2d_f32(&P.tmA[p], pr[p].X, (uint64_t)BK, (uint64_t)(pr[p].k / BK) * (uint64_t)pr[p].n, (uint64_t)BK * 4, BK, BM)) return 4;
+      LLMREC_CHECK_ARG(pr[p].k % BK == 0 && (int64_t)(pr[p].k / BK) * npad < (int64_t)INT32_MAX, "proj_fwd: panel layout needs k %% 32 == 0 and (k/32)*n < 2^31");
+      if (!make_tmap_2d_f32(&P.tmA[p], pr[p].X, (uint64_t)BK, (uint64_t)(pr[p].k / BK) * (uint64_t)npad, (uint64_t)BK * 4, BK, BM)) return 4;
     } else if (!make_tmap_2d_f32(&P.tmA[p], pr[p].X, (uint64_t)pr[p].k, (uint64_t)pr[p].n, (uint64_t)pr[p].ldx * 4, BK, BM)) return 4;
-    P.prob[p].panel = panel ? 1 : 0;
+    P.prob[p].panel = panel ? (int)npad : 0;
     if (!make_tmap_2d_f32(&P.tmW[p], wsrc, (uint64_t)pr[p].k, (uint64_t)(split ? 2 * d : d), (uint64_t)pr[p].k * 4, BK, (uint32_t)d)) return 4;
     P.prob[p].n = (int)pr[p].n; P.prob[p].k = pr[p].k; P.prob[p].kblocks = (pr[p].k + BK - 1) / BK;
     P.prob[p].tile_start = tiles; P.prob[p].ldy = pr[p].ldy; P.prob[p].Y = pr[p].Y; P.prob[p].bias = pr[p].bias;
@@ -565,9 +566,10 @@ int proj_wgrad_tc_group(const llmrec_proj_wgrad_problem* pr, int n_prob, int d, 
   C.d = d;
   for (int p = 0; p < n_prob; ++p) {
     const bool panel = (pr[p].accumulate & LLMREC_WGRAD_X_PANELS) != 0;
+    const int64_t npad = LLMREC_PANEL_ROWS(pr[p].n);
     if (panel) {
-      LLMREC_CHECK_ARG(pr[p].k % BK == 0 && (int64_t)(pr[p].k / BK + 4) * pr[p].n < (int64_t)INT32_MAX, "proj_wgrad: panel layout needs k %% 32 == 0 and (k/32 + 4)*n < 2^31");
-      if (!make_tmap_2d_f32(&P.tmX[p], pr[p].X, (uint64_t)32, (uint64_t)(pr[p].k / 32) * (uint64_t)pr[p].n, (uint64_t)128, 32, BK, true)) return 4;
+      LLMREC_CHECK_ARG(pr[p].k % BK == 0 && (int64_t)(pr[p].k / BK + 4) * npad < (int64_t)INT32_MAX, "proj_wgrad: panel layout needs k %% 32 == 0 and (k/32 + 4)*n < 2^31");
+      if (!make_tmap_2d_f32(&P.tmX[p], pr[p].X, (uint64_t)32, (uint64_t)(pr[p].k / 32) * (uint64_t)npad, (uint64_t)128, 32, BK, true)) return 4;
     } else if (!make_tmap_2d_f32(&P.tmX[p], pr[p].X, (uint64_t)pr[p].k, (uint64_t)pr[p].n, (uint64_t)pr[p].ldx * 4, 32, BK, true)) return 4;
     if (!make_tmap_2d_f32(&P.tmG[p], pr[p].dY, (uint64_t)d, (uint64_t)pr[p].n, (uint64_t)pr[p].lddy * 4, 32, BK, true)) return 4;
     WgProblem& w = P.prob[p];
@@ -575,7 +577,7 @@ int proj_wgrad_tc_group(const llmrec_proj_wgrad_problem* pr, int n_prob, int d, 
     w.rows_per_chunk = wg_rows_per_chunk(pr[p].n);
     w.chunks = (int)((pr[p].n + w.rows_per_chunk - 1) / w.rows_per_chunk);
     w.item_start = items;
-    w.panel = panel ? 1 : 0;
+    w.panel = panel ? (int)npad : 0;
     items += w.ft_tiles * w.chunks;
     C.dY[p] = pr[p].dY; C.ld[p] = pr[p].lddy; C.n[p] = pr[p].n; C.db[p] = pr[p].db; C.acc[p] = pr[p].accumulate & LLMREC_WGRAD_ACCUMULATE;
   }

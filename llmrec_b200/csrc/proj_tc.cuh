@@ -10,7 +10,7 @@ constexpr int BM = 128;  // tile rows (fwd) / tile features (wgrad) = UMMA M
 constexpr int BK = 32;   // fp32 per 128-byte swizzle row
 constexpr uint32_t kTileA = BM * BK * 4;  // 16 KiB
 
-struct FwdProblem { int n, k, kblocks, tile_start; long long ldy; float* Y; const float* bias; int panel; /* X in column panels */ };
+struct FwdProblem { int n, k, kblocks, tile_start; long long ldy; float* Y; const float* bias; int panel; /* 0 = row-major X, else rows per column panel (n rounded up to 128) */ };
 struct FwdParams {
   CUtensorMap tmA[kMaxProb];
   CUtensorMap tmW[kMaxProb];  // [2d x k] (hi rows then lo rows) when SPLIT, [d x k] otherwise
@@ -19,7 +19,7 @@ struct FwdParams {
 };
 
 
-struct WgProblem { int n, k, ft_tiles, chunks, rows_per_chunk, item_start, panel; };
+struct WgProblem { int n, k, ft_tiles, chunks, rows_per_chunk, item_start, panel; /* 0 = row-major X, else rows per column panel */ };
 struct WgParams {
   CUtensorMap tmX[kMaxProb];
   CUtensorMap tmG[kMaxProb];

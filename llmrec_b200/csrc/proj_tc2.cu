@@ -69,8 +69,8 @@ __global__ void __launch_bounds__(512, 1) proj_fwd_ts_kernel(const __grid_consta
       for (int kb = 0; kb < kb_n; ++kb) {
         mbar_wait(&empty[st.stage], st.phase ^ 1);
         mbar_arrive_expect_tx(&full[st.stage], stage_bytes);
-        // panels: tile (panel kb, rows mblk*BM..) is one contiguous 16 KiB run; rows past n read the next panel (finite, never stored)
-        if (P.prob[p].panel) tma_load_2d(sA(st.stage), &P.tmA[p], &full[st.stage], 0, kb * P.prob[p].n + mblk * BM);
+        // panels: tile (panel kb, rows mblk*BM..) is one contiguous 16 KiB run (panels are zero-padded to a multiple of 128 rows)
+        if (P.prob[p].panel) tma_load_2d(sA(st.stage), &P.tmA[p], &full[st.stage], 0, kb * P.prob[p].panel + mblk * BM);
         else tma_load_2d(sA(st.stage), &P.tmA[p], &full[st.stage], kb * BK, mblk * BM);
         tma_load_2d(sB(st.stage), &P.tmW[p], &full[st.stage], kb * BK, 0);
         tma_load_2d(sBlo(st.stage), &P.tmW[p], &full[st.stage], kb * BK, d);
@@ -244,8 +244,8 @@ __global__ void __launch_bounds__(512, 1) proj_wgrad_ts_kernel(const __grid_cons
         const int r = r0 + kb * BK;
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
-          // panels: rows past n read the next panel, where dY's box is zero-filled -> they add exactly 0
-          if (P.prob[p].panel) tma_load_2d(sA(st.stage) + a * 4096, &P.tmX[p], &full[st.stage], 0, (ft * 4 + a) * P.prob[p].n + r);
+          // panels: one contiguous 4 KiB run per box; rows past n are the panel's zero padding, panels past k/32 are out of bounds (zero fill)
+          if (P.prob[p].panel) tma_load_2d(sA(st.stage) + a * 4096, &P.tmX[p], &full[st.stage], 0, (ft * 4 + a) * P.prob[p].panel + r);
           else tma_load_2d(sA(st.stage) + a * 4096, &P.tmX[p], &full[st.stage], ft * BM + a * 32, r);
         }
         for (int b = 0; b < d / 32; ++b) tma_load_2d(sB(st.stage) + b * 4096, &P.tmG[p], &full[st.stage], b * 32, r);

@@ -45,14 +45,14 @@ __global__ void __launch_bounds__(256) scatter_add_rows_kernel(const float* __re
   if (r < 0) return;
   for (int j = lane; j < d; j += 32) atomicAdd(Y + (int64_t)r * ldy + j, G[(int64_t)b * ldg + j]);
 }
-// Xp[(p*n + r)*32 + c] = X[r*ldx + 32p + c]: one float4 per thread, 128-byte segments on both sides
-__global__ void __launch_bounds__(256) panelize_kernel(const float* __restrict__ X, int64_t ldx, int64_t n, int panels, float* __restrict__ Xp) {
-  const int64_t total = n * (int64_t)panels * 8;   // float4 count
+// Xp[(p*npad + r)*32 + c] = r < n ? X[r*ldx + 32p + c] : 0: one float4 per thread, 128-byte segments on both sides
+__global__ void __launch_bounds__(256) panelize_kernel(const float* __restrict__ X, int64_t ldx, int64_t n, int64_t npad, int panels, float* __restrict__ Xp) {
+  const int64_t total = npad * (int64_t)panels * 8;   // float4 count
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int q = (int)(i & 7);
-    const int64_t row = i >> 3;                    // output row = p*n + r
-    const int64_t p = row / n, r = row - p * n;
-    reinterpret_cast<float4*>(Xp)[i] = __ldg(reinterpret_cast<const float4*>(X + r * ldx + p * 32) + q);
+    const int64_t row = i >> 3;                       // output row = p*npad + r
+    const int64_t p = row / npad, r = row - p * npad;
+    reinterpret_cast<float4*>(Xp)[i] = r < n ? __ldg(reinterpret_cast<const float4*>(X + r * ldx + p * 32) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 }  // namespace llmrec
@@ -62,10 +62,11 @@ extern "C" int llmrec_panelize_f32(const float* X, int64_t ldx, int64_t n, int32
   LLMREC_REQUIRE_DEVICE();
   LLMREC_CHECK_ARG(k >= 32 && k % 32 == 0 && ldx >= k && ldx % 4 == 0 && aligned16(X) && aligned16(Xp), "panelize: k %% 32 == 0, ldx %% 4 == 0 and 16-byte aligned pointers required");
   if (n <= 0) return 0;
-  const int64_t total = n * (int64_t)(k / 32) * 8;
+  const int64_t npad = LLMREC_PANEL_ROWS(n);
+  const int64_t total = npad * (int64_t)(k / 32) * 8;
   int64_t blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  panelize_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(X, ldx, n, k / 32, Xp);
+  panelize_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(X, ldx, n, npad, k / 32, Xp);
   LLMREC_CHECK_LAUNCH("panelize");
   return 0;
 }

@@ -143,7 +143,8 @@ def _get_scratch(key, n, device):
 
 class PanelFeat:
     """A constant feature table X[n x k] re-laid out by llmrec_panelize_f32 (LLMREC_X_PANELS): k/32 column panels, each a
-    contiguous [n x 32] block, so the [rows x 32] tiles of the projection kernels are contiguous DRAM runs."""
+    contiguous [n_pad x 32] block (n rounded up to 128, zero padded), so the [rows x 32] tiles of the projection kernels
+    are contiguous DRAM runs."""
 
     def __init__(self, X):
         _mat(X)
@@ -151,14 +152,15 @@ class PanelFeat:
         if k % 32:
             raise ValueError("panel layout needs k % 32 == 0")
         self.shape, self.device = (n, k), X.device
-        self.data = torch.empty((k // 32) * n, 32, dtype=torch.float32, device=X.device)
+        self.n_pad = (n + 127) // 128 * 128
+        self.data = torch.empty((k // 32) * self.n_pad, 32, dtype=torch.float32, device=X.device)
         N.check(N.lib().llmrec_panelize_f32(_p(X), _ld(X), n, k, _p(self.data), _stream()), "panelize")
         _count()
 
     def rows(self):
         """back to row-major [n x k] (tests)"""
         n, k = self.shape
-        return self.data.view(k // 32, n, 32).permute(1, 0, 2).reshape(n, k).contiguous()
+        return self.data.view(k // 32, self.n_pad, 32)[:, :n].permute(1, 0, 2).reshape(n, k).contiguous()
 
 
 def _x_operand(X):

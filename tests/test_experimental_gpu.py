@@ -22,8 +22,10 @@ def test_panelize_round_trip(n, k):
     wide = torch.randn(n, k + 8, generator=g).to(cuda)
     X = wide[:, 4:4 + k]                                   # leading dimension != k
     P = ops.PanelFeat(X)
-    assert P.shape == (n, k) and tuple(P.data.shape) == ((k // 32) * n, 32)
+    n_pad = (n + 127) // 128 * 128
+    assert P.shape == (n, k) and tuple(P.data.shape) == ((k // 32) * n_pad, 32)
     assert torch.equal(P.rows(), X.contiguous())
+    assert float(P.data.view(k // 32, n_pad, 32)[:, n:].abs().sum()) == 0.0          # zero padding
 
 
 # tails on purpose: n % 128 != 0 (fwd row tiles), n % 32 != 0 (wgrad row blocks), k % 128 != 0 (wgrad feature tiles)
