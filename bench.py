@@ -166,16 +166,15 @@ def run_ours(a):
     # ---- end-to-end leg through Trainer's API ------------------------------------------------------------
     loss_host = torch.empty(K, dtype=torch.float32).pin_memory()
     for _ in range(3):
-        tr.train_batch(*tr.sample_batch())
+        tr.train_next_batch()
     torch.cuda.synchronize()
     e0.record()
     n_e2e = 0
     h2d = 0
     for i in range(K):
-        u, p, n = tr.sample_batch()
-        loss = tr.train_batch(u, p, n)
+        loss, B = tr.train_next_batch()          # the body of Trainer.train()'s loop: host sampler -> pinned staging -> H2D -> step
         loss_host[i:i + 1].copy_(loss, non_blocking=True)
-        n_e2e += len(u); h2d += 3 * 4 * len(u)
+        n_e2e += B; h2d += 3 * 4 * B
     e1.record()
     torch.cuda.synchronize()
     ms_e2e = e0.elapsed_time(e1)

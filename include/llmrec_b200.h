@@ -227,6 +227,24 @@ int llmrec_host_sample_items(uint32_t* mt_key /* [624] */, int32_t* mt_pos, cons
                              const int32_t* train_rowptr, const int32_t* train_col, int32_t n_items,
                              int32_t* pos_out, int32_t* neg_out);
 
+/* One whole training batch on the host, bit-identical to Data.sample() followed by the augmented-edge step of
+ * main.py:213-224, written straight into a (pinned) [3 x ld] int32 staging buffer (rows: users, pos, neg):
+ *   users    random.sample(exist_users, batch) -- or `batch` random.choice draws when batch > n_exist (load_data.py:158-161)
+ *            -- from CPython's MT19937 stream (random.getstate(): key[624] + pos)
+ *   pos/neg  the np.random.randint draws of llmrec_host_sample_items from numpy's legacy global stream
+ *   aug      random.sample(users, n_aug) over the batch list; (u, aug_pos[u], aug_neg[u]) appended when both ids < aug_limit
+ *            (the column count of train_mat, main.py:84-85,221);
+ *            INT32_MIN in the tables = uid missing from augmented_sample_dict (KeyError upstream -> return 4)
+ * `*_pool_branch` = which branch of CPython's sample() applies (n <= setsize), decided by the caller in Python arithmetic.
+ * stamp: int32[n_exist] zero-initialised once, `epoch` > 0 and different on every call; pool: int32[max(n_exist if
+ * users_pool_branch, 0) and >= batch + n_aug].  *n_out = batch + kept augmented edges.  All pointers HOST. */
+int llmrec_host_sample_batch(uint32_t* py_key, int32_t* py_pos, uint32_t* np_key, int32_t* np_pos,
+                             const int32_t* exist_users, int32_t n_exist, int32_t batch, int32_t users_pool_branch,
+                             const int32_t* train_rowptr, const int32_t* train_col, int32_t n_items,
+                             int32_t n_aug, int32_t aug_pool_branch, const int32_t* aug_pos, const int32_t* aug_neg,
+                             int32_t n_aug_table, int32_t aug_limit, int32_t* stamp, int32_t epoch, int32_t* pool,
+                             int32_t* out, int64_t ld, int32_t* n_out);
+
 /* Row helpers of the sharded (multi-GPU) path: epilogue of an item-side propagation applied AFTER the cross-rank
  * sum of per-rank partials, and gather / scatter-add of batch rows by index (idx < 0 = row not owned: zeros / skipped). */
 int llmrec_row_scale_softmax_f32(const float* X, int64_t ldx, const float* scale, float* Y, int64_t ldy, int64_t n, int32_t d,

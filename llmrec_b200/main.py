@@ -45,6 +45,16 @@ def set_seed(seed):
         torch.cuda.manual_seed_all(seed)
 
 
+class _StagingSlot:
+    """One pinned [3 x cap] int32 index buffer + the event recorded after its H2D copy.  A slot is rewritten only after
+    that copy has completed, so the host may run ahead of the device by at most the ring length."""
+
+    def __init__(self, cap):
+        self.host = torch.empty((3, cap), dtype=torch.int32).pin_memory()
+        self.np = self.host.numpy()
+        self.event = torch.cuda.Event()
+
+
 def _stack_rows(obj):
     """indexable[n] -> ndarray [n x dim] (main.py:61-65, 73-77)."""
     if isinstance(obj, np.ndarray):
@@ -104,7 +114,16 @@ class Trainer(object):
         self.hot = self.model_mm.hot_path(self.ui_graph, self.iu_graph)
         # torch.optim.AdamW defaults: betas (0.9, 0.999), eps 1e-8, weight_decay 0.01 (main.py:100-104)
         self.optimizer = self.hot.set_optimizer(lr=self.lr)
-        self._idx_host = None
+        self._slots, self._slot_i, self._idx_dev = [], 0, None
+        # whole batches (users, items, augmented edges) from one C call, same `random` / `np.random` streams (host_native.BatchSampler)
+        self._batch_sampler = None
+        if getattr(data_generator, "_sampler", "python") == "native":
+            from .host_native import BatchSampler
+            rowptr, col = data_generator.csr("train")
+            aug_pos, aug_neg = BatchSampler.aug_tables(self.augmented_sample_dict, data_generator.n_users)
+            self._batch_sampler = BatchSampler(data_generator.exist_users, rowptr, col, data_generator.n_items, data_generator.batch_size,
+                                               aug_pos, aug_neg, aug_limit=self.n_items)
+            self._batch_np = np.empty((3, 2 * data_generator.batch_size + 8), dtype=np.int32)
         self.use_graph = bool(getattr(args, "cuda_graph", 1))
         self._epoch_stats = torch.zeros(3, dtype=torch.float32, device=self.device)
 
@@ -159,7 +178,12 @@ class Trainer(object):
 
     # ---- one batch ---------------------------------------------------------------------------------------
     def sample_batch(self):
-        """Data.sample() + augmented edges (main.py:213-224); host side, reference RNG order."""
+        """Data.sample() + augmented edges (main.py:213-224); host side, reference RNG order.  -> three lists."""
+        if self._batch_sampler is not None:
+            o = self._batch_np
+            B = self._batch_sampler.draw(o, self.args.aug_sample_rate)
+            self.new_batch_size = B - self._batch_sampler.batch
+            return o[0, :B].tolist(), o[1, :B].tolist(), o[2, :B].tolist()
         users, pos_items, neg_items = self.data_generator.sample()
         aug = self.augmented_sample_dict
         ni = self.n_items
@@ -171,27 +195,59 @@ class Trainer(object):
         neg_items = neg_items + [aug[u][1] for u in keep]
         return users, pos_items, neg_items
 
-    def upload_batch(self, users, pos_items, neg_items):
-        """[3 x B'] int32 through pinned memory; returns three device views."""
-        B = len(users)
-        if self._idx_host is None or self._idx_host.shape[1] < B:
-            self._idx_host = torch.empty((3, max(B, 2 * self.batch_size)), dtype=torch.int32).pin_memory()
-            self._idx_dev = torch.empty_like(self._idx_host, device=self.device)
-        h = self._idx_host
-        h[0, :B] = torch.as_tensor(users, dtype=torch.int32)
-        h[1, :B] = torch.as_tensor(pos_items, dtype=torch.int32)
-        h[2, :B] = torch.as_tensor(neg_items, dtype=torch.int32)
-        self._idx_dev[:, :B].copy_(h[:, :B], non_blocking=True)
+    def _next_slot(self, need):
+        """Next pinned staging slot of the ring (4 slots), free to be rewritten."""
+        cap = max(need, 2 * self.batch_size + 8)
+        if not self._slots or self._slots[0].host.shape[1] < cap:
+            if self._slots:
+                torch.cuda.synchronize()                                  # copies out of the old ring may still be in flight
+            self._slots = [_StagingSlot(cap) for _ in range(4)]
+            self._idx_dev = torch.empty((3, cap), dtype=torch.int32, device=self.device)
+            self._slot_i = 0
+        slot = self._slots[self._slot_i]
+        self._slot_i = (self._slot_i + 1) % len(self._slots)
+        slot.event.synchronize()                                          # its previous H2D copy has completed
+        return slot
+
+    def _push(self, slot, B):
+        self._idx_dev[:, :B].copy_(slot.host[:, :B], non_blocking=True)
+        slot.event.record()
         d = self._idx_dev
         return d[0, :B], d[1, :B], d[2, :B]
 
-    def train_batch(self, users, pos_items, neg_items):
-        u, p, n = self.upload_batch(users, pos_items, neg_items)
+    def upload_batch(self, users, pos_items, neg_items):
+        """[3 x B'] int32 through pinned memory; returns three device views."""
+        B = len(users)
+        slot = self._next_slot(B)
+        slot.np[0, :B] = users
+        slot.np[1, :B] = pos_items
+        slot.np[2, :B] = neg_items
+        return self._push(slot, B)
+
+    def stage_batch(self):
+        """sample_batch + upload_batch without the Python lists in between: the C sampler writes the batch straight into
+        a pinned staging slot.  -> three device views (users, pos, neg)."""
+        if self._batch_sampler is None:
+            return self.upload_batch(*self.sample_batch())
+        slot = self._next_slot(2 * self._batch_sampler.batch)
+        B = self._batch_sampler.draw(slot.np, self.args.aug_sample_rate)
+        self.new_batch_size = B - self._batch_sampler.batch
+        return self._push(slot, B)
+
+    def _step(self, u, p, n):
         loss = self.hot.train_step_graphed(u, p, n) if self.use_graph else self.hot.train_step(u, p, n)
         # device-side epoch accumulators: [total, mf(main), emb(main)]
         self._epoch_stats[0:1] += loss
         self._epoch_stats[1:3] += self.hot.head_out[0:2]
         return loss
+
+    def train_batch(self, users, pos_items, neg_items):
+        return self._step(*self.upload_batch(users, pos_items, neg_items))
+
+    def train_next_batch(self):
+        """One iteration of the training loop (main.py:213-278): draw the next batch, run the step.  -> (loss tensor, B')."""
+        u, p, n = self.stage_batch()
+        return self._step(u, p, n), int(u.numel())
 
     # ---- training loop (main.py:189-326) -----------------------------------------------------------------
     def train(self):
@@ -206,9 +262,7 @@ class Trainer(object):
             self.n_interactions = 0
             self.model_mm.train()
             for _ in range(n_batch):
-                users, pos_items, neg_items = self.sample_batch()
-                self.train_batch(users, pos_items, neg_items)
-                self.n_interactions += len(users)
+                self.n_interactions += self.train_next_batch()[1]
             loss, mf_loss, emb_loss = (float(x) for x in self._epoch_stats.tolist())      # the one sync per epoch
             reg_loss, contrastive_loss = 0.0, 0.0
             if math.isnan(loss):
