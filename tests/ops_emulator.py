@@ -1,0 +1,146 @@
+"""Torch-CPU stand-ins for the subset of `llmrec_b200.ops` that the ID-only engines (engine.HotPath(feats=None),
+dist.ShardedHotPath) call.  TEST INFRASTRUCTURE ONLY: it lets the host-side orchestration of those engines -- buffer
+ping-pong, exchange structure, index arithmetic, optimizer sharding -- run under world-size-2 gloo on a machine without
+a GPU.  The product never imports this file; `install()` monkeypatches a test process.  Semantics follow
+include/llmrec_b200.h, each function naming the entry point it stands in for."""
+import torch
+import torch.distributed as dist
+
+
+class CsrOperator:
+    """llmrec_spmm_csr_f32:  Y = epi(diag(rs) . P(vals) . diag(cs) . X) + Z,  epi = row softmax when flagged."""
+
+    def __init__(self, rowptr, col, n_rows, n_cols, vals=None, rs=None, cs=None, tile_nnz=0, plan=None):
+        self.rowptr, self.col, self.vals, self.rs, self.cs = rowptr.long(), col.long(), vals, rs, cs
+        self.n_rows, self.n_cols, self.nnz = int(n_rows), int(n_cols), int(col.numel())
+        self.plan = plan if plan is not None else object()
+        assert self.rowptr.numel() == self.n_rows + 1
+
+    def apply(self, segs):
+        rp = self.rowptr
+        rows = torch.repeat_interleave(torch.arange(self.n_rows), rp[1:] - rp[:-1])
+        e = torch.arange(int(rp[0]), int(rp[-1]))
+        c = self.col[e]
+        w = torch.ones(e.numel()) if self.vals is None else self.vals[e].clone()
+        if self.cs is not None:
+            w = w * self.cs[c]
+        for X, Y, Z, sm in segs:
+            assert X.shape[0] == self.n_cols and Y.shape[0] == self.n_rows
+            acc = torch.zeros(self.n_rows, X.shape[1]).index_add_(0, rows, X[c] * w[:, None])
+            if self.rs is not None:
+                acc = acc * self.rs[:, None]
+            if sm:
+                acc = torch.softmax(acc, dim=-1)
+            if Z is not None:
+                acc = acc + Z
+            Y.copy_(acc)
+
+
+def row_scale_softmax(X, scale, out, softmax):           # llmrec_row_scale_softmax_f32
+    y = X * scale[:, None] if scale is not None else X.clone()
+    out.copy_(torch.softmax(y, dim=-1) if softmax else y)
+    return out
+
+
+def row_softmax_bwd(S, dS, out=None):                    # llmrec_row_softmax_bwd_f32
+    r = S * (dS - (S * dS).sum(-1, keepdim=True))
+    if out is None:
+        return r
+    out.copy_(r)
+    return out
+
+
+def fuse_fwd(layers, sides, coefs, out, rows=None):      # llmrec_fuse_fwd_f32 (ID-only: no normalised side terms)
+    assert not sides
+    m = sum(layers) / len(layers)
+    if rows is None:
+        out.copy_(m)
+    else:
+        out[rows.long()] = m[rows.long()]
+    return out
+
+
+def fuse_bwd(g, n_layers, d_layer, sides, coefs, d_sides, accumulate, rows=None):   # llmrec_fuse_bwd_f32
+    assert not sides and rows is None
+    if d_layer is not None:
+        d_layer.copy_(g / n_layers)
+
+
+def gather_rows(X, idx, out):                            # llmrec_gather_rows_f32: idx < 0 -> zeros
+    i = idx.long()
+    out.copy_(torch.where((i >= 0)[:, None], X[i.clamp(min=0)], torch.zeros(1)))
+    return out
+
+
+def scatter_add_rows(G, idx, Y):                         # llmrec_scatter_add_rows_f32: idx < 0 skipped
+    i = idx.long()
+    keep = i >= 0
+    Y.index_add_(0, i[keep], G[keep])
+
+
+def bpr_work(n_heads, B, device):
+    return torch.zeros(1)
+
+
+def bpr_heads(heads, users, pos, neg, n_keep, regs0_over_bs, out, loss, work):      # llmrec_bpr_heads_f32
+    u, p, n = users.long(), pos.long(), neg.long()
+    for h, (XU, XI, GU, GI, w_mf, w_emb) in enumerate(heads):
+        a = XU[u].clone().requires_grad_(True)
+        b = XI[p].clone().requires_grad_(True)
+        c = XI[n].clone().requires_grad_(True)
+        maxi = torch.nn.functional.logsigmoid((a * b).sum(1) - (a * c).sum(1) + 1e-8)
+        keep = torch.argsort(maxi.detach(), stable=True)[:n_keep]
+        mf = -maxi[keep].mean()
+        emb = regs0_over_bs * (1 / (2 * a.pow(2).sum() + 1e-8) + 1 / (2 * b.pow(2).sum() + 1e-8) + 1 / (2 * c.pow(2).sum() + 1e-8))
+        (w_mf * mf + w_emb * emb).backward()
+        if GU is not None:
+            GU.index_add_(0, u, a.grad)
+        if GI is not None:
+            GI.index_add_(0, p, b.grad)
+            GI.index_add_(0, n, c.grad)
+        loss += (w_mf * mf + w_emb * emb).detach()
+        out[4 * h:4 * h + 3] = torch.tensor([float(mf), float(emb), float(n_keep)])
+
+
+class AdamW:                                             # llmrec_adamw_advance + llmrec_adamw_step_f32 (torch.optim.AdamW defaults)
+    def __init__(self, params, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01):
+        self.params, self.lr, self.betas, self.eps, self.wd = list(params), lr, betas, eps, weight_decay
+        self.m = [torch.zeros_like(p) for p in self.params]
+        self.v = [torch.zeros_like(p) for p in self.params]
+        self.t = 0
+
+    def step(self, grads):
+        self.t += 1
+        b1, b2 = self.betas
+        for p, g, m, v in zip(self.params, grads, self.m, self.v):
+            p.mul_(1 - self.lr * self.wd)
+            m.mul_(b1).add_(g, alpha=1 - b1)
+            v.mul_(b2).addcmul_(g, g, value=1 - b2)
+            denom = (v.sqrt() / (1 - b2 ** self.t) ** 0.5).add_(self.eps)
+            p.addcdiv_(m, denom, value=-self.lr / (1 - b1 ** self.t))
+
+
+def install():
+    """Patch llmrec_b200.ops / llmrec_b200.dist in THIS process; add gloo stand-ins for the two NCCL-only collectives."""
+    import sys
+    import llmrec_b200.ops as ops
+    import llmrec_b200.dist as D
+    me = sys.modules[__name__]
+    for name in ("CsrOperator", "row_scale_softmax", "row_softmax_bwd", "fuse_fwd", "fuse_bwd", "gather_rows", "scatter_add_rows",
+                 "bpr_work", "bpr_heads", "AdamW"):
+        setattr(ops, name, getattr(me, name))
+    D.CsrOperator = CsrOperator
+
+    def reduce_scatter_tensor(out, inp, group=None):
+        t = inp.clone()
+        dist.all_reduce(t, group=group)
+        r, n = dist.get_rank(group), out.shape[0]
+        out.copy_(t[r * n:(r + 1) * n])
+
+    def all_gather_into_tensor(out, inp, group=None):
+        parts = [torch.empty_like(inp) for _ in range(dist.get_world_size(group))]
+        dist.all_gather(parts, inp.clone(), group=group)
+        out.copy_(torch.cat(parts))
+
+    D.dist.reduce_scatter_tensor = reduce_scatter_tensor
+    D.dist.all_gather_into_tensor = all_gather_into_tensor
