@@ -56,8 +56,8 @@ def test_torch(ua_embeddings, ia_embeddings, users_to_test, is_val, drop_flag=Fa
     result = {"precision": np.zeros(nK), "recall": np.zeros(nK), "ndcg": np.zeros(nK), "hit_ratio": np.zeros(nK), "auc": 0.0}
     if get_args().test_flag != "part":
         raise NotImplementedError("test_flag='full' (AUC over the whole ranking, batch_test.py:38-68) is out of scope (SURVEY.md 8f-4)")
-    test_users = list(users_to_test)
-    n_test_users = len(test_users)
+    test_users = np.asarray(list(users_to_test) if not isinstance(users_to_test, np.ndarray) else users_to_test, dtype=np.int32)
+    n_test_users = int(test_users.shape[0])
     u_batch_size = BATCH_SIZE * 2                                             # batch_test.py:117
     if ops.SCORE_MODE.get(getattr(get_args(), "proj_mode", "3xtf32"), 0) != 2:
         u_batch_size = max(u_batch_size, 32768)       # no score block is materialised: larger user blocks, same results
@@ -73,11 +73,11 @@ def test_torch(ua_embeddings, ia_embeddings, users_to_test, is_val, drop_flag=Fa
     for user_batch, hits in pending:                                          # one D2H per block, after all launches
         h = hits.cpu().numpy()
         trp = data_generator.csr("val" if is_val else "test")[0]
-        ub = np.asarray(user_batch, dtype=np.int64)
-        n_pos = (trp[ub + 1] - trp[ub]).astype(np.int64)                       # len(truth[u]) per user
-        m = metrics.block_metrics(h, n_pos, Ks)
+        n_pos = (trp[user_batch + 1] - trp[user_batch]).astype(np.int64)       # len(truth[u]) per user
+        rows, m = metrics.block_metrics_sparse(h, n_pos, Ks)
         for k in ("precision", "recall", "ndcg", "hit_ratio"):
-            # sequential float64 accumulation in user order == the reference's `+= re[k] / n` loop (:160-165)
+            # sequential float64 accumulation in user order == the reference's `+= re[k] / n` loop (:160-165); users without a
+            # hit contribute exactly +0.0, which leaves the accumulator's bits unchanged, so only the others are walked
             acc = np.cumsum(np.vstack([result[k][None, :], m[k] / n_test_users]), axis=0)
             result[k] = acc[-1]
         count += len(user_batch)

@@ -65,29 +65,52 @@ def _ideal_dcg_table(K):
     return _IDEAL_CACHE[K]
 
 
-def block_metrics(hits, n_pos, Ks):
+def block_metrics_sparse(hits, n_pos, Ks):
     """hits: uint8 [n x K_max] (rank order), n_pos: int [n] = len(test_set[u]).
-    Returns dict of float64 [n x len(Ks)] arrays: precision, recall, ndcg, hit_ratio -- per user bit-identical to
-    precision_at_k / recall_at_k / ndcg_at_k / hit_at_k (hits are 0/1, so means and sums are exact integer ratios; the
-    ideal DCG of "m hits inside the retrieved list" comes from a table built with the scalar expression)."""
-    hits = np.ascontiguousarray(hits)
+    -> (rows, m): rows = ascending indices of the users with at least one hit in the retrieved list, m = dict of float64
+    [len(rows) x len(Ks)] arrays precision / recall / ndcg / hit_ratio for those users; every other user's metrics are
+    exactly 0.0.  Per user bit-identical to precision_at_k / recall_at_k / ndcg_at_k / hit_at_k: hits are 0/1, so means and
+    sums are exact integer ratios; DCG is the scalar expression evaluated on the user's row; the ideal DCG of "m hits inside
+    the retrieved list" comes from a table built with the scalar expression.  Work beyond one word-wise scan of the hit matrix is proportional to the number of users WITH hits."""
+    hits = np.ascontiguousarray(hits, dtype=np.uint8)
     n, kmax = hits.shape
-    npos = np.asarray(n_pos, dtype=np.float64)
-    total_hits = hits.sum(axis=1, dtype=np.int64)                      # hits inside the whole retrieved list
-    out = {k: np.zeros((n, len(Ks))) for k in ("precision", "recall", "ndcg", "hit_ratio")}
+    # users with any hit: OR-reduce each row as 64-bit words (rows padded to a multiple of 8 bytes)
+    w = -(-kmax // 8) * 8
+    if w != kmax:
+        padded = np.zeros((n, w), dtype=np.uint8)
+        padded[:, :kmax] = hits
+    else:
+        padded = hits
+    rows = np.flatnonzero(np.bitwise_or.reduce(padded.view(np.uint64), axis=1)) if n else np.zeros(0, dtype=np.int64)
+    out = {k: np.zeros((rows.size, len(Ks))) for k in ("precision", "recall", "ndcg", "hit_ratio")}
+    if rows.size == 0:
+        return rows, out
+    sub = hits[rows]                                                   # [len(rows) x K_max]
+    total_hits = sub.sum(axis=1, dtype=np.int64)                       # hits inside the whole retrieved list
+    npos = np.asarray(n_pos, dtype=np.float64)[rows]
     for j, K in enumerate(Ks):
         K = min(K, kmax)
-        head = hits[:, :K]
+        head = sub[:, :K]
         cnt = head.sum(axis=1, dtype=np.int64)
         cntf = cnt.astype(np.float64)
         out["precision"][:, j] = cntf / K
         with np.errstate(divide="ignore", invalid="ignore"):
             out["recall"][:, j] = np.where(npos == 0, 0.0, cntf / npos)
         out["hit_ratio"][:, j] = (cnt > 0).astype(np.float64)
-        rows = np.nonzero(cnt)[0]                                      # dcg is 0 (and ndcg 0) without a hit in the head
-        if rows.size:
+        live = np.nonzero(cnt)[0]                                      # dcg is 0 (and ndcg 0) without a hit in the head
+        if live.size:
             disc = np.log2(np.arange(2, K + 2))
-            dcg = np.sum(np.ascontiguousarray(head[rows]).astype(np.float64) / disc, axis=1)
-            best = _ideal_dcg_table(K)[np.minimum(total_hits[rows], K)]
-            out["ndcg"][rows, j] = dcg / best
+            dcg = np.sum(np.ascontiguousarray(head[live]).astype(np.float64) / disc, axis=1)
+            best = _ideal_dcg_table(K)[np.minimum(total_hits[live], K)]
+            out["ndcg"][live, j] = dcg / best
+    return rows, out
+
+
+def block_metrics(hits, n_pos, Ks):
+    """Dense form of block_metrics_sparse: dict of float64 [n x len(Ks)] arrays."""
+    rows, m = block_metrics_sparse(hits, n_pos, Ks)
+    n = np.asarray(hits).shape[0]
+    out = {k: np.zeros((n, len(Ks))) for k in m}
+    for k in m:
+        out[k][rows] = m[k]
     return out
