@@ -1,0 +1,24 @@
+#!/bin/bash
+# First GPU call after a round that ended without GPU budget: validates everything that was written on the CPU side and
+# produces the A/B numbers DESIGN.md 7 asks for, all on ONE box (box-to-box variance is +-30 %, only same-call numbers compare).
+#   gpurun --timeout 1500 -- 'bash tools/next_gpu_call.sh'
+# Outputs land in gpurun_out/next/.
+set -u
+cd "$(dirname "$0")/.."
+O=gpurun_out/next
+mkdir -p $O
+python -m llmrec_b200.build > $O/build.log 2>&1
+echo "== validated suite" ;      timeout 900 python -m pytest tests -q -m gpu -x > $O/pytest_gpu.log 2>&1; tail -2 $O/pytest_gpu.log
+echo "== experimental suite" ;   LLMREC_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_experimental_gpu.py -q -m gpu > $O/pytest_experimental.log 2>&1; tail -3 $O/pytest_experimental.log
+echo "== fetch-pattern ceilings"; bash tools/build_tma_stream.sh > /dev/null 2>&1 && timeout 300 ./tools/tma_stream > $O/tma_stream.txt 2>&1; sort -k9 -n -r $O/tma_stream.txt | head -8
+echo "== bench rows";            timeout 400 python bench.py --no-cpu > $O/bench_rows.json 2> $O/bench_rows.err; cut -c1-400 $O/bench_rows.json
+echo "== bench panels";          timeout 400 python bench.py --no-cpu --feat_layout panels > $O/bench_panels.json 2> $O/bench_panels.err; cut -c1-400 $O/bench_panels.json
+python - <<'PY'
+import json
+for name in ("rows", "panels"):
+    try:
+        j = json.loads([l for l in open(f"gpurun_out/next/bench_{name}.json") if l.startswith("{")][0])
+        print(name, "ms/step", j["ms_per_step"], "e2e ms", j["e2e"]["ms_per_step"], "families", j["roofline"]["families_ms"], "eval users/s", j.get("eval", {}).get("value"))
+    except Exception as e:
+        print(name, "no line:", e)
+PY
