@@ -21,3 +21,20 @@ for name, op, seg in (("ui (gather items)", g.ui, [(Xi, Yu, None, False)]), ("iu
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 3
     print(f"variant={os.environ.get('LLMREC_SPMM_VARIANT','0')} tile={op.plan.tile_nnz} {name}: {ms:.3f} ms  gather {(g.nnz * (4 * d + 4)) / ms / 1e6:.0f} GB/s  nnz={g.nnz} tiles={op.plan.n_tiles} split={op.plan.n_split}", flush=True)
+
+# Column windows: the item table ([ni x 128] fp32 = 512 MB at full scale) does not fit the 126 MB L2, a 32-column window of it
+# (128 MB) nearly does.  Same product as W launches over column slices (views with the full leading dimension): more index
+# traffic (col re-read per window) against a higher L2 hit rate on the gathered rows.  COLWIN="2,4" to try.
+for W in [int(x) for x in os.environ.get("COLWIN", "").split(",") if x]:
+    w = d // W
+    for name, op, X, Y in (("ui (gather items)", g.ui, Xi, Yu), ("iu (gather users)", g.iu_raw, Xu, Yi)):
+        ref = torch.empty_like(Y)
+        op.apply([(X, ref, None, False)])
+        run = lambda: [op.apply([(X[:, j * w:(j + 1) * w], Y[:, j * w:(j + 1) * w], None, False)]) for j in range(W)]
+        run(); torch.cuda.synchronize()
+        same = bool(torch.equal(Y, ref))
+        e0.record()
+        for _ in range(3):
+            run()
+        e1.record(); torch.cuda.synchronize()
+        print(f"colwin={W} {name}: {e0.elapsed_time(e1) / 3:.3f} ms  identical={same}", flush=True)
