@@ -1,5 +1,4 @@
-"""Torch-CPU stand-ins for the subset of `llmrec_b200.ops` that the ID-only engines (engine.HotPath(feats=None),
-dist.ShardedHotPath) call.  TEST INFRASTRUCTURE ONLY: it lets the host-side orchestration of those engines -- buffer
+"""Torch-CPU stand-ins for the subset of `llmrec_b200.ops` that the engines (engine.HotPath, dist.ShardedHotPath) call.  TEST INFRASTRUCTURE ONLY: it lets the host-side orchestration of those engines -- buffer
 ping-pong, exchange structure, index arithmetic, optimizer sharding -- run under world-size-2 gloo on a machine without
 a GPU.  The product never imports this file; `install()` monkeypatches a test process.  Semantics follow
 include/llmrec_b200.h, each function naming the entry point it stands in for."""
@@ -50,9 +49,14 @@ def row_softmax_bwd(S, dS, out=None):                    # llmrec_row_softmax_bw
     return out
 
 
-def fuse_fwd(layers, sides, coefs, out, rows=None):      # llmrec_fuse_fwd_f32 (ID-only: no normalised side terms)
-    assert not sides
+def _unit(x):
+    return x / x.norm(dim=1, keepdim=True).clamp_min(1e-12)           # F.normalize(x, p=2, dim=1)
+
+
+def fuse_fwd(layers, sides, coefs, out, rows=None):      # llmrec_fuse_fwd_f32
     m = sum(layers) / len(layers)
+    for x, c in zip(sides, coefs):
+        m = m + c * _unit(x)
     if rows is None:
         out.copy_(m)
     else:
@@ -61,9 +65,32 @@ def fuse_fwd(layers, sides, coefs, out, rows=None):      # llmrec_fuse_fwd_f32 (
 
 
 def fuse_bwd(g, n_layers, d_layer, sides, coefs, d_sides, accumulate, rows=None):   # llmrec_fuse_bwd_f32
-    assert not sides and rows is None
+    assert rows is None
     if d_layer is not None:
         d_layer.copy_(g / n_layers)
+    for x, c, dx in zip(sides, coefs, d_sides):
+        y = _unit(x)
+        t = c * (g - y * (y * g).sum(1, keepdim=True)) / x.norm(dim=1, keepdim=True).clamp_min(1e-12)
+        dx.copy_(dx + t if accumulate else t)
+
+
+def proj_fwd_group(problems, d, mode=0):                 # llmrec_proj_fwd_group_f32
+    for X, W, b, out in problems:
+        out.copy_(X @ W.t() + (b if b is not None else 0.0))
+
+
+def proj_wgrad_group(problems, d, mode=0):               # llmrec_proj_wgrad_group_f32
+    for X, dY, dW, db, acc in problems:
+        gw, gb = dY.t() @ X, dY.sum(0)
+        dW.copy_(dW + gw if acc else gw)
+        if db is not None:
+            db.copy_(db + gb if acc else gb)
+
+
+def sqnorm_grad(X, G, c, accumulate, loss):              # llmrec_sqnorm_grad_f32
+    loss += c * 0.5 * X.pow(2).sum()
+    if G is not None:
+        G.copy_(G + c * X if accumulate else c * X)
 
 
 def gather_rows(X, idx, out):                            # llmrec_gather_rows_f32: idx < 0 -> zeros
@@ -126,10 +153,12 @@ def install():
     import llmrec_b200.ops as ops
     import llmrec_b200.dist as D
     me = sys.modules[__name__]
+    import llmrec_b200.graph as G
     for name in ("CsrOperator", "row_scale_softmax", "row_softmax_bwd", "fuse_fwd", "fuse_bwd", "gather_rows", "scatter_add_rows",
-                 "bpr_work", "bpr_heads", "AdamW"):
+                 "bpr_work", "bpr_heads", "AdamW", "proj_fwd_group", "proj_wgrad_group", "sqnorm_grad"):
         setattr(ops, name, getattr(me, name))
     D.CsrOperator = CsrOperator
+    G.CsrOperator = CsrOperator
 
     def reduce_scatter_tensor(out, inp, group=None):
         t = inp.clone()
