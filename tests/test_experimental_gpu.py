@@ -182,3 +182,18 @@ def test_fullsize_scoring_topk_properties():
     assert bool((picked[:, :-1] >= picked[:, 1:] - 1e-5).all())                                      # descending
     S.scatter_(1, idx.long(), float("-inf"))
     assert bool((S.max(dim=1).values <= picked[:, -1] + 1e-5).all())                                 # nothing outside beats the K-th
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_sharded_feature_path_equals_engine(world):
+    """dist_feat.ShardedFeatureHotPath (side features, users and item tables sharded) == engine.HotPath."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    here = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, os.path.join(here, "dist_feat_gpu_check.py")] if world == 1 else \
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+         "--master-port", "29523", os.path.join(here, "dist_feat_gpu_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert "DIST_FEAT_CHECK_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
