@@ -1,59 +1,74 @@
 """Command-line flags of the reference (utility/parser.py:4-56), same names, types and defaults.
 
-Table-driven restatement: (flag, kwargs) rows instead of one add_argument call per line.
+Table-driven restatement: typed tables of (default, meaning) instead of one add_argument call per flag.
 `--mask` keeps the reference's `type=bool` quirk (any non-empty string is True, parser.py:39).
 `--dataset netflix|movielens` are accepted as aliases of the on-disk directory names
 (README.md:80-82 documents the short names; main.py:69-72 only handles the long ones).
 """
 import argparse
 
-_FLAGS = [
-    ("data_path", dict(nargs="?", default="./data/", help="Input data path")),
-    ("seed", dict(type=int, default=2022, help="Random seed")),
-    ("dataset", dict(nargs="?", default="netflix", help="Choose a dataset from {movieLens, netflix}")),
-    ("verbose", dict(type=int, default=5, help="Interval of evaluation.")),
-    ("epoch", dict(type=int, default=1000, help="Number of epoch.")),
-    ("regs", dict(nargs="?", default="[1e-5,1e-5,1e-2]", help="Regularizations.")),
-    ("embed_size", dict(type=int, default=64, help="Embedding size.")),
-    ("weight_size", dict(nargs="?", default="[64, 64]", help="Output sizes of every layer")),
-    ("early_stopping_patience", dict(type=int, default=7, help="Early Stop Patience")),
-    ("mess_dropout", dict(nargs="?", default="[0.1, 0.1]", help="Keep probability w.r.t. message dropout")),
-    ("sparse", dict(type=int, default=1, help="Sparse or dense adjacency matrix")),
-    ("debug", dict(action="store_true")),
-    ("norm_type", dict(nargs="?", default="sym", help="Adjacency matrix normalization operation")),
-    ("gpu_id", dict(type=int, default=0, help="GPU ID")),
-    ("Ks", dict(nargs="?", default="[10, 20, 50]", help="K value of ndcg/recall @ k")),
-    ("test_flag", dict(nargs="?", default="part", help="Specify the test type from {part, full}")),
-    ("sc", dict(type=float, default=1.0, help="GCN self connection")),
-    ("feat_reg_decay", dict(default=1e-5, type=float, help="Feature Reg Decay")),
-    ("title", dict(default="try_to_draw_line", type=str, help="")),
-    ("cf_model", dict(nargs="?", default="lightgcn", help="Downstream Collaborative Filtering model")),
-    ("point", dict(default="", type=str, help="")),
-    # train
-    ("batch_size", dict(type=int, default=1024, help="Batch size.")),
-    ("lr", dict(type=float, default=0.0001, help="Learning rate.")),
-    ("de_lr", dict(type=float, default=0.0002, help="Decoder learning rate.")),
-    ("weight_decay", dict(default=1e-4, type=float, help="Weight_decay")),
-    # model
-    ("layers", dict(type=int, default=1, help="Number of graph conv layers")),
-    ("drop_rate", dict(type=float, default=0.0, help="Dropout rate")),
-    ("mask_rate", dict(type=float, default=0.0, help="Mask rate")),
-    ("mask", dict(type=bool, default=False, help="If mask")),
-    ("user_cat_rate", dict(type=float, default=2.8, help="User cat rate")),
-    ("item_cat_rate", dict(type=float, default=0.005, help="Item cat rate")),
-    ("model_cat_rate", dict(type=float, default=0.02, help="Model cat rate")),
-    ("de_drop1", dict(default=0.31, type=float, help="for D model2")),
-    ("de_drop2", dict(default=0.5, type=float, help="")),
-    # loss
-    ("aug_mf_rate", dict(type=float, default=0.012, help="Augmentation mf rate")),
-    ("prune_loss_drop_rate", dict(type=float, default=0.71, help="Prune loss drop rate")),
-    ("mm_mf_rate", dict(type=float, default=0.0001, help="MM mf rate")),
-    ("feat_loss_type", dict(default="sce", type=str, help="Feature loss type")),
-    ("att_re_rate", dict(type=float, default=0.00000, help="Attribute restoration rate")),
-    ("alpha_l", dict(type=float, default=2, help="`pow`inddex for `sce` loss")),
-    ("aug_sample_rate", dict(type=float, default=0.1, help="Augmentation sample rate")),
-    ("mf_emb_rate", dict(type=float, default=0.0, help="MF embedding rate")),
-]
+# name -> (default, what it controls).  Grouped by how argparse converts the value; defaults are the reference's.
+_INT = {
+    "seed": (2022, "seed of random / numpy / torch"),
+    "verbose": (5, "evaluate every this many epochs"),
+    "epoch": (1000, "maximum number of epochs"),
+    "embed_size": (64, "width d of the id embeddings and of every projected feature"),
+    "early_stopping_patience": (7, "evaluations without a better recall@20 before stopping"),
+    "sparse": (1, "unused by LLMRec (kept for CLI compatibility)"),
+    "gpu_id": (0, "CUDA device"),
+    "batch_size": (1024, "sampled interactions per step (augmented edges come on top)"),
+    "layers": (1, "unused by LLMRec: the layer count is len(weight_size)"),
+}
+_FLOAT = {
+    "sc": (1.0, "unused by LLMRec"),
+    "feat_reg_decay": (1e-5, "weight of the squared-norm regulariser on the propagated image/text features"),
+    "lr": (0.0001, "AdamW learning rate"),
+    "de_lr": (0.0002, "learning rate of the (unused) decoder optimiser"),
+    "weight_decay": (1e-4, "unused: AdamW runs with torch's default 0.01"),
+    "drop_rate": (0.0, "feature dropout (only 0 is supported here)"),
+    "mask_rate": (0.0, "share of nodes whose features are masked (mask branch, not supported here)"),
+    "user_cat_rate": (2.8, "fusion weight of the normalised user-profile term"),
+    "item_cat_rate": (0.005, "fusion weight of each normalised item-attribute term"),
+    "model_cat_rate": (0.02, "fusion weight of the normalised image and text terms"),
+    "de_drop1": (0.31, "unused"),
+    "de_drop2": (0.5, "unused"),
+    "aug_mf_rate": (0.012, "weight of the attribute BPR heads"),
+    "prune_loss_drop_rate": (0.71, "share of the batch dropped by prune_loss (the least negative log-sigmoids)"),
+    "mm_mf_rate": (0.0001, "weight of the image and text BPR heads"),
+    "att_re_rate": (0.00000, "weight of the attribute-restoration loss (mask branch)"),
+    "alpha_l": (2, "exponent of the sce restoration loss (mask branch)"),
+    "aug_sample_rate": (0.1, "share of the batch's users that contribute an LLM-augmented edge"),
+    "mf_emb_rate": (0.0, "unused"),
+}
+_OPTIONAL_TEXT = {                     # nargs="?": python-literal strings are eval()ed by the trainer, like upstream
+    "data_path": ("./data/", "directory that holds the dataset directories"),
+    "dataset": ("netflix", "netflix | movielens, or the on-disk directory name"),
+    "regs": ("[1e-5,1e-5,1e-2]", "regs[0] scales the reciprocal-norm embedding term"),
+    "weight_size": ("[64, 64]", "one entry per propagation layer"),
+    "mess_dropout": ("[0.1, 0.1]", "unused by LLMRec"),
+    "norm_type": ("sym", "unused by LLMRec"),
+    "Ks": ("[10, 20, 50]", "cut-offs of recall / precision / hit / ndcg"),
+    "test_flag": ("part", "part = top-K metrics; full (with AUC) is not supported here"),
+    "cf_model": ("lightgcn", "name used in the log file name"),
+}
+_TEXT = {
+    "title": ("try_to_draw_line", "free text"),
+    "point": ("", "free text"),
+    "feat_loss_type": ("sce", "mse | sce (mask branch)"),
+}
+
+
+def _reference_flags():
+    rows = [(k, dict(type=int, default=v, help=h)) for k, (v, h) in _INT.items()]
+    rows += [(k, dict(type=float, default=v, help=h)) for k, (v, h) in _FLOAT.items()]
+    rows += [(k, dict(nargs="?", default=v, help=h)) for k, (v, h) in _OPTIONAL_TEXT.items()]
+    rows += [(k, dict(type=str, default=v, help=h)) for k, (v, h) in _TEXT.items()]
+    rows.append(("debug", dict(action="store_true", help="do not write ./logs/")))
+    rows.append(("mask", dict(type=bool, default=False, help="bool('...'): ANY non-empty value switches the mask branch on (upstream quirk)")))
+    return rows
+
+
+_FLAGS = _reference_flags()
 
 # B200-side extras (not in the reference; all optional)
 _EXTRA = [
