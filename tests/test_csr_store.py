@@ -98,7 +98,7 @@ def test_large_store_loads_without_parsing(tmp_path):
     users, pos, neg = d.sample()
     assert len(users) == 1024 and all(p in d.train_items[u] for u, p in zip(users, pos))
     assert all(n not in d.train_items[u] for u, n in zip(users, neg))
-    assert dt < 5.0, dt
+    assert dt < 15.0, dt          # ~0.5 s here; the json walk of the same data takes minutes
 
 
 def test_store_shards_tile_the_graph(tmp_path):
