@@ -206,8 +206,15 @@ def run_ours(a):
     hbm, tf, src = peaks()
     top = max((k for k in fam if k in bytes_), key=lambda k: fam[k])
     ach = bytes_[top] / (fam[top] * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    try:                                          # per-launch DRAM bytes of this kernel family from the committed ncu capture
+        t = json.load(open(os.path.join(REPO, "profiles", "r1_ncu_traffic.json"))).get(top)
+        if t and a.workload == "netflix":
+            traffic, traffic_src = int(t["bytes"]), t["source"]
+    except Exception:
+        pass
     roof = {"kernel": top, "bound": "hbm", "achieved": round(ach, 1), "peak": hbm, "unit": "GB/s", "frac": round(ach / hbm, 4),
-            "traffic": None, "peak_source": src, "alg_bytes_per_step": bytes_[top], "ms_per_step": round(fam[top], 4),
+            "traffic": traffic, "traffic_source": traffic_src, "peak_source": src, "alg_bytes_per_step": bytes_[top], "ms_per_step": round(fam[top], 4),
             "families_ms": {k: round(v, 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1])},
             "families_gbs": {k: round(bytes_[k] / (fam[k] * 1e-3) / 1e9, 1) for k in fam if k in bytes_}}
 
