@@ -54,6 +54,12 @@ class _HotPathFn(torch.autograd.Function):
         return (None,) + tuple(grads[n].clone() for n in PARAM_ORDER)
 
 
+def _on_device(t):
+    """The kernels take device pointers: parameters must live on the GPU (the orchestration tests substitute this check together
+    with the kernels, tests/ops_emulator.py)."""
+    return t.is_cuda
+
+
 class MM_Model(nn.Module):
     def __init__(self, n_users, n_items, embedding_dim, weight_size, dropout_list, image_feats, text_feats,
                  user_init_embedding, item_attribute_dict):
@@ -96,7 +102,7 @@ class MM_Model(nn.Module):
         key = (id(ui_graph), id(iu_graph), self.user_id_embedding.weight.data_ptr())
         if self._hp is None or self._hp_key != key:
             args = get_args()
-            if not self.user_id_embedding.weight.is_cuda:
+            if not _on_device(self.user_id_embedding.weight):
                 raise RuntimeError("MM_Model runs on the B200 kernels only: move it to CUDA first (no CPU path)")
             ui_f, ui_b = operators_from_coo(ui_graph)
             iu_f, iu_b = operators_from_coo(iu_graph)

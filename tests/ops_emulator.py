@@ -129,6 +129,30 @@ def bpr_heads(heads, users, pos, neg, n_keep, regs0_over_bs, out, loss, work):  
         out[4 * h:4 * h + 3] = torch.tensor([float(mf), float(emb), float(n_keep)])
 
 
+def score_topk(U, I, users, mask_rowptr, mask_col, K, mode=0, want_vals=False):     # llmrec_score_topk_f32
+    """exact fp32 scores, train items excluded, ties -> lowest item id, -1 past the last candidate"""
+    u = users.long()
+    S = U[u] @ I.t()
+    rp = mask_rowptr.long()
+    rows = torch.repeat_interleave(torch.arange(rp.numel() - 1), rp[1:] - rp[:-1])
+    dense = torch.zeros(rp.numel() - 1, I.shape[0], dtype=torch.bool)
+    dense[rows, mask_col.long()] = True
+    S = S.masked_fill(dense[u], float("-inf"))
+    val, idx = torch.sort(S, dim=1, descending=True, stable=True)
+    val, idx = val[:, :K], idx[:, :K].to(torch.int32)
+    idx = torch.where(torch.isinf(val), torch.full_like(idx, -1), idx)
+    return (idx, val) if want_vals else idx
+
+
+def topk_hits(idx, users, truth_rowptr, truth_col):      # llmrec_topk_hits
+    rp, col = truth_rowptr.long(), truth_col.long()
+    out = torch.zeros(idx.shape, dtype=torch.uint8)
+    for b, u in enumerate(users.long().tolist()):
+        truth = set(col[rp[u]:rp[u + 1]].tolist())
+        out[b] = torch.tensor([1 if int(i) in truth else 0 for i in idx[b].tolist()], dtype=torch.uint8)
+    return out
+
+
 class AdamW:                                             # llmrec_adamw_advance + llmrec_adamw_step_f32 (torch.optim.AdamW defaults)
     def __init__(self, params, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01):
         self.params, self.lr, self.betas, self.eps, self.wd = list(params), lr, betas, eps, weight_decay
@@ -155,7 +179,7 @@ def install():
     me = sys.modules[__name__]
     import llmrec_b200.graph as G
     for name in ("CsrOperator", "row_scale_softmax", "row_softmax_bwd", "fuse_fwd", "fuse_bwd", "gather_rows", "scatter_add_rows",
-                 "bpr_work", "bpr_heads", "AdamW", "proj_fwd_group", "proj_wgrad_group", "sqnorm_grad"):
+                 "bpr_work", "bpr_heads", "AdamW", "proj_fwd_group", "proj_wgrad_group", "sqnorm_grad", "score_topk", "topk_hits"):
         setattr(ops, name, getattr(me, name))
     D.CsrOperator = CsrOperator
     G.CsrOperator = CsrOperator
