@@ -10,7 +10,7 @@ mkdir -p $O
 python -m llmrec_b200.build > $O/build.log 2>&1
 echo "== validated suite" ;      timeout 900 python -m pytest tests -q -m gpu -x > $O/pytest_gpu.log 2>&1; tail -2 $O/pytest_gpu.log
 echo "== experimental suite" ;   LLMREC_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_experimental_gpu.py -q -m gpu > $O/pytest_experimental.log 2>&1; tail -3 $O/pytest_experimental.log
-echo "== fetch-pattern ceilings"; bash tools/build_tma_stream.sh > /dev/null 2>&1 && timeout 300 ./tools/tma_stream > $O/tma_stream.txt 2>&1; sort -k9 -n -r $O/tma_stream.txt | head -8
+echo "== fetch-pattern ceilings"; bash tools/build_tma_stream.sh > /dev/null 2>&1 && timeout 400 ./tools/tma_stream > $O/tma_stream.txt 2>&1; cat $O/tma_stream.txt
 echo "== bench rows";            timeout 400 python bench.py --no-cpu > $O/bench_rows.json 2> $O/bench_rows.err; cut -c1-400 $O/bench_rows.json
 echo "== bench panels";          timeout 400 python bench.py --no-cpu --feat_layout panels > $O/bench_panels.json 2> $O/bench_panels.err; cut -c1-400 $O/bench_panels.json
 python - <<'PY'

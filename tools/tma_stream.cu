@@ -44,6 +44,40 @@ __global__ void __launch_bounds__(64, 1) stream_kernel(const __grid_constant__ S
   }
   __syncthreads();
   const int kb_n = P.k / 32;
+  if (P.layout >= 3) {
+    // proj_wgrad's pattern: work item = (2048-row chunk, 128-feature tile); per stage FOUR [32 rows x 32 floats] boxes
+    // (layout 3: row-major X -> 32 x 512 B at the row pitch; layout 4: panel form -> four contiguous 4 KiB runs)
+    const int ft_n = P.k / 128, chunks = (int)((P.n + 2047) / 2048);
+    if (threadIdx.x == 0) {
+      PipeState st(P.stages);
+      for (int item = blockIdx.x; item < ft_n * chunks; item += gridDim.x) {
+        const int chunk = item / ft_n, ft = item - chunk * ft_n;
+        const long long r0 = (long long)chunk * 2048, r1 = r0 + 2048 < P.n ? r0 + 2048 : P.n;
+        for (long long r = r0; r < r1; r += 32) {
+          mbar_wait(&empty[st.stage], st.phase ^ 1);
+          uint8_t* dst = smem + (size_t)st.stage * box_bytes;
+          mbar_arrive_expect_tx(&full[st.stage], 16384u);
+          for (int a = 0; a < 4; ++a) {
+            if (P.layout == 4) tma_load_2d(dst + a * 4096, &P.tm, &full[st.stage], 0, (int)((long long)(ft * 4 + a) * P.n + r));
+            else tma_load_2d(dst + a * 4096, &P.tm, &full[st.stage], ft * 128 + a * 32, (int)r);
+          }
+          st.advance();
+        }
+      }
+    } else if (threadIdx.x == 32) {
+      PipeState st(P.stages);
+      for (int item = blockIdx.x; item < ft_n * chunks; item += gridDim.x) {
+        const int chunk = item / ft_n;
+        const long long r0 = (long long)chunk * 2048, r1 = r0 + 2048 < P.n ? r0 + 2048 : P.n;
+        for (long long r = r0; r < r1; r += 32) {
+          mbar_wait(&full[st.stage], st.phase);
+          mbar_arrive(&empty[st.stage]);
+          st.advance();
+        }
+      }
+    }
+    return;
+  }
   if (threadIdx.x == 0) {
     PipeState st(P.stages);
     for (int tile = blockIdx.x; tile < P.tiles; tile += gridDim.x) {
@@ -141,5 +175,28 @@ int main(int argc, char** argv) {
           printf("%s box %3d rows  stages %2d  ctas %3d  %8.3f ms  %8.1f GB/s\n", names[layout], rows, stages, ctas, ms, bytes / ms * 1e-6);
         }
       }
+  // proj_wgrad's fetch pattern (stage = four 32 x 32 boxes = 16 KiB; rows of a tail block past n are zero-filled, so the
+  // expected byte count stays 16 KiB)
+  for (int layout = 3; layout <= 4; ++layout)
+    for (int stages : {4, 6, 8, 12}) {
+      std::vector<StreamParams> P(tables);
+      bool ok = true;
+      for (int t = 0; t < tables; ++t) {
+        StreamParams& p = P[t];
+        p.base = X[t]; p.n = n; p.k = k; p.rows = 128; p.stages = stages; p.layout = layout; p.tiles = 0;
+        if (layout == 3) ok = ok && make_tmap_2d_f32(&p.tm, X[t], (uint64_t)k, (uint64_t)n, (uint64_t)k * 4, 32, 32, true);
+        else ok = ok && make_tmap_2d_f32(&p.tm, X[t], 32, (uint64_t)(k / 32) * (uint64_t)n, 128, 32, 32, true);
+      }
+      if (!ok) { printf("tensor map failed: %s\n", llmrec_last_error()); return 1; }
+      const size_t smem = (size_t)stages * 16384 + 1024 + 256;
+      cudaFuncSetAttribute(stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      for (int ctas : {148, 296}) {
+        if (ctas == 296 && smem > 100 * 1024) continue;
+        float ms = time_ms(st, 20, [&] { for (int t = 0; t < tables; ++t) stream_kernel<<<ctas, 64, smem, st>>>(P[t]); });
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { printf("kernel failed: %s\n", cudaGetErrorString(e)); return 1; }
+        printf("%s 4 x [32 x 32] boxes  stages %2d  ctas %3d  %8.3f ms  %8.1f GB/s\n", layout == 3 ? "wgrad rows  " : "wgrad panels", stages, ctas, ms, bytes / ms * 1e-6);
+      }
+    }
   return 0;
 }
