@@ -128,10 +128,11 @@ __global__ void __launch_bounds__(384, 1) proj_fwd_tc_kernel(const __grid_consta
         mbar_wait(&empty[st.stage], st.phase ^ 1);
         mbar_arrive_expect_tx(&full[st.stage], kTileA + b_bytes * (SPLIT ? 2u : 1u));
         // panels: tile (panel kb, rows mblk*BM..) is one contiguous 16 KiB run (panels are zero-padded to a multiple of 128 rows)
-        if (P.prob[p].panel) tma_load_2d(sA(st.stage), &P.tmA[p], &full[st.stage], 0, kb * P.prob[p].panel + mblk * BM);
-        else tma_load_2d(sA(st.stage), &P.tmA[p], &full[st.stage], kb * BK, mblk * BM);
-        tma_load_2d(sB(st.stage), &P.tmW[p], &full[st.stage], kb * BK, 0);
-        if (SPLIT) tma_load_2d(sBlo(st.stage), &P.tmW[p], &full[st.stage], kb * BK, d);
+        const int kbe = P.krot ? (kb + (int)blockIdx.x) % kb_n : kb;   // which k-block this stage holds (the sum over k is order-free)
+        if (P.prob[p].panel) tma_load_2d(sA(st.stage), &P.tmA[p], &full[st.stage], 0, kbe * P.prob[p].panel + mblk * BM);
+        else tma_load_2d(sA(st.stage), &P.tmA[p], &full[st.stage], kbe * BK, mblk * BM);
+        tma_load_2d(sB(st.stage), &P.tmW[p], &full[st.stage], kbe * BK, 0);
+        if (SPLIT) tma_load_2d(sBlo(st.stage), &P.tmW[p], &full[st.stage], kbe * BK, d);
         st.advance();
       }
     }
@@ -522,6 +523,8 @@ int proj_fwd_tc_group(const llmrec_proj_fwd_problem* pr, int n_prob, int d, int 
     tiles += (int)((pr[p].n + BM - 1) / BM);
   }
   P.total_tiles = tiles;
+  static const bool krot = getenv("LLMREC_PROJ_KROT") != nullptr;
+  P.krot = krot ? 1 : 0;
   uint32_t smem;
   P.stages = stages_for(d, split, &smem);
   P.tmem_cols = (int)pow2_cols(2 * d);

@@ -13,9 +13,13 @@ echo "== experimental suite" ;   LLMREC_TEST_EXPERIMENTAL=1 timeout 600 python -
 echo "== fetch-pattern ceilings"; bash tools/build_tma_stream.sh > /dev/null 2>&1 && timeout 400 ./tools/tma_stream > $O/tma_stream.txt 2>&1; cat $O/tma_stream.txt
 echo "== bench rows";            timeout 400 python bench.py --no-cpu > $O/bench_rows.json 2> $O/bench_rows.err; cut -c1-400 $O/bench_rows.json
 echo "== bench panels";          timeout 400 python bench.py --no-cpu --feat_layout panels > $O/bench_panels.json 2> $O/bench_panels.err; cut -c1-400 $O/bench_panels.json
+echo "== k-rotation (LLMREC_PROJ_KROT=1): concurrent CTAs read different feature columns"
+LLMREC_PROJ_KROT=1 timeout 300 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "projection" > $O/pytest_krot.log 2>&1; tail -1 $O/pytest_krot.log
+LLMREC_PROJ_KROT=1 timeout 400 python bench.py --no-cpu > $O/bench_rows_krot.json 2> $O/bench_rows_krot.err
+LLMREC_PROJ_KROT=1 timeout 400 python bench.py --no-cpu --feat_layout panels > $O/bench_panels_krot.json 2> $O/bench_panels_krot.err
 python - <<'PY'
 import json
-for name in ("rows", "panels"):
+for name in ("rows", "panels", "rows_krot", "panels_krot"):
     try:
         j = json.loads([l for l in open(f"gpurun_out/next/bench_{name}.json") if l.startswith("{")][0])
         print(name, "ms/step", j["ms_per_step"], "e2e ms", j["e2e"]["ms_per_step"], "families", j["roofline"]["families_ms"], "eval users/s", j.get("eval", {}).get("value"))
