@@ -24,6 +24,7 @@ struct StreamParams {
   long long n;
   int k, rows, stages, layout;   // layout: 0 rows, 1 panels, 2 bulk (panel form)
   int tiles;                     // row tiles = ceil(n / rows)
+  int rot;                       // 1: CTA b starts its k loop at block b mod (k/32)
 };
 
 __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -82,7 +83,8 @@ __global__ void __launch_bounds__(64, 1) stream_kernel(const __grid_constant__ S
     PipeState st(P.stages);
     for (int tile = blockIdx.x; tile < P.tiles; tile += gridDim.x) {
       const long long r0 = (long long)tile * P.rows;
-      for (int kb = 0; kb < kb_n; ++kb) {
+      for (int kb0 = 0; kb0 < kb_n; ++kb0) {
+        const int kb = P.rot ? (kb0 + (int)blockIdx.x) % kb_n : kb0;
         mbar_wait(&empty[st.stage], st.phase ^ 1);
         void* dst = smem + (size_t)st.stage * box_bytes;
         if (P.layout == 2) {
@@ -175,6 +177,26 @@ int main(int argc, char** argv) {
           printf("%s box %3d rows  stages %2d  ctas %3d  %8.3f ms  %8.1f GB/s\n", names[layout], rows, stages, ctas, ms, bytes / ms * 1e-6);
         }
       }
+  // k rotation (LLMREC_PROJ_KROT): same boxes, but concurrent CTAs sit at different feature columns
+  for (int layout = 0; layout < 2; ++layout)
+    for (int stages : {6, 12}) {
+      std::vector<StreamParams> P(tables);
+      bool ok = true;
+      for (int t = 0; t < tables; ++t) {
+        StreamParams& p = P[t];
+        p.base = X[t]; p.n = n; p.k = k; p.rows = 128; p.stages = stages; p.layout = layout; p.rot = 1;
+        p.tiles = (int)((n + 127) / 128);
+        if (layout == 0) ok = ok && make_tmap_2d_f32(&p.tm, X[t], (uint64_t)k, (uint64_t)n, (uint64_t)k * 4, 32, 128);
+        else ok = ok && make_tmap_2d_f32(&p.tm, X[t], 32, (uint64_t)(k / 32) * (uint64_t)n, 128, 32, 128);
+      }
+      if (!ok) { printf("tensor map failed: %s\n", llmrec_last_error()); return 1; }
+      const size_t smem = (size_t)stages * 16384 + 1024 + 256;
+      cudaFuncSetAttribute(stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      float ms = time_ms(st, 20, [&] { for (int t = 0; t < tables; ++t) stream_kernel<<<148, 64, smem, st>>>(P[t]); });
+      cudaError_t e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) { printf("kernel failed: %s\n", cudaGetErrorString(e)); return 1; }
+      printf("%s box 128 rows  stages %2d  ctas 148  k-rotated  %8.3f ms  %8.1f GB/s\n", names[layout], stages, ms, bytes / ms * 1e-6);
+    }
   // proj_wgrad's fetch pattern (stage = four 32 x 32 boxes = 16 KiB; rows of a tail block past n are zero-filled, so the
   // expected byte count stays 16 KiB)
   for (int layout = 3; layout <= 4; ++layout)
