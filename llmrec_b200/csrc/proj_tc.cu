@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(384, 1) proj_fwd_tc_kernel(const __grid_consta
         if (P.prob[p].panel) tma_load_2d(sA(st.stage), &P.tmA[p], &full[st.stage], 0, kbe * P.prob[p].panel + mblk * BM);
         else tma_load_2d(sA(st.stage), &P.tmA[p], &full[st.stage], kbe * BK, mblk * BM);
         tma_load_2d(sB(st.stage), &P.tmW[p], &full[st.stage], kbe * BK, 0);
-        if (SPLIT) tma_load_2d(sBlo(st.stage), &P.tmW[p], &full[st.stage], kbe * BK, d);
+        if (SPLIT && !P.wbox) tma_load_2d(sBlo(st.stage), &P.tmW[p], &full[st.stage], kbe * BK, d);
         st.advance();
       }
     }
@@ -500,6 +500,9 @@ int proj_fwd_tc_group(const llmrec_proj_fwd_problem* pr, int n_prob, int d, int 
   memset(&P, 0, sizeof(P));
   P.n_prob = n_prob; P.d = d;
   int tiles = 0;
+  static const bool wbox_env = getenv("LLMREC_PROJ_WBOX") != nullptr;
+  const bool wbox = wbox_env && split && 2 * d <= 256;          // TMA boxes hold at most 256 rows
+  P.wbox = wbox ? 1 : 0;
   for (int p = 0; p < n_prob; ++p) {
     const float* wsrc = split ? pr[p].wsplit : pr[p].W;
     LLMREC_CHECK_ARG(!split || pr[p].wsplit, "proj_fwd: 3xTF32 mode needs a wsplit buffer of 2*d*k floats");
@@ -517,7 +520,7 @@ int proj_fwd_tc_group(const llmrec_proj_fwd_problem* pr, int n_prob, int d, int 
       if (!make_tmap_2d_f32(&P.tmA[p], pr[p].X, (uint64_t)BK, (uint64_t)(pr[p].k / BK) * (uint64_t)npad, (uint64_t)BK * 4, BK, BM)) return 4;
     } else if (!make_tmap_2d_f32(&P.tmA[p], pr[p].X, (uint64_t)pr[p].k, (uint64_t)pr[p].n, (uint64_t)pr[p].ldx * 4, BK, BM)) return 4;
     P.prob[p].panel = panel ? (int)npad : 0;
-    if (!make_tmap_2d_f32(&P.tmW[p], wsrc, (uint64_t)pr[p].k, (uint64_t)(split ? 2 * d : d), (uint64_t)pr[p].k * 4, BK, (uint32_t)d)) return 4;
+    if (!make_tmap_2d_f32(&P.tmW[p], wsrc, (uint64_t)pr[p].k, (uint64_t)(split ? 2 * d : d), (uint64_t)pr[p].k * 4, BK, (uint32_t)(wbox ? 2 * d : d))) return 4;
     P.prob[p].n = (int)pr[p].n; P.prob[p].k = pr[p].k; P.prob[p].kblocks = (pr[p].k + BK - 1) / BK;
     P.prob[p].tile_start = tiles; P.prob[p].ldy = pr[p].ldy; P.prob[p].Y = pr[p].Y; P.prob[p].bias = pr[p].bias;
     tiles += (int)((pr[p].n + BM - 1) / BM);

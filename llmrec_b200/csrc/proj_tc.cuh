@@ -16,6 +16,7 @@ struct FwdParams {
   CUtensorMap tmW[kMaxProb];  // [2d x k] (hi rows then lo rows) when SPLIT, [d x k] otherwise
   FwdProblem prob[kMaxProb];
   int n_prob, total_tiles, d, stages, tmem_cols;
+  int wbox;   // experiment (LLMREC_PROJ_WBOX): W_hi and W_lo of a k-block arrive as ONE [2d x 32] TMA box (they are adjacent rows of the split matrix and adjacent in the stage)
   int krot;   // experiment (LLMREC_PROJ_KROT): CTA b starts its k loop at block b mod kblocks, so concurrent CTAs read different columns
 };
 

@@ -73,8 +73,8 @@ __global__ void __launch_bounds__(512, 1) proj_fwd_ts_kernel(const __grid_consta
         const int kbe = P.krot ? (kb + (int)blockIdx.x) % kb_n : kb;   // which k-block this stage holds (the sum over k is order-free)
         if (P.prob[p].panel) tma_load_2d(sA(st.stage), &P.tmA[p], &full[st.stage], 0, kbe * P.prob[p].panel + mblk * BM);
         else tma_load_2d(sA(st.stage), &P.tmA[p], &full[st.stage], kbe * BK, mblk * BM);
-        tma_load_2d(sB(st.stage), &P.tmW[p], &full[st.stage], kbe * BK, 0);
-        tma_load_2d(sBlo(st.stage), &P.tmW[p], &full[st.stage], kbe * BK, d);
+        tma_load_2d(sB(st.stage), &P.tmW[p], &full[st.stage], kbe * BK, 0);      // wbox: this one box is [2d x 32] = W_hi | W_lo
+        if (!P.wbox) tma_load_2d(sBlo(st.stage), &P.tmW[p], &full[st.stage], kbe * BK, d);
         st.advance();
       }
     }

@@ -17,9 +17,12 @@ echo "== k-rotation (LLMREC_PROJ_KROT=1): concurrent CTAs read different feature
 LLMREC_PROJ_KROT=1 timeout 300 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "projection" > $O/pytest_krot.log 2>&1; tail -1 $O/pytest_krot.log
 LLMREC_PROJ_KROT=1 timeout 400 python bench.py --no-cpu > $O/bench_rows_krot.json 2> $O/bench_rows_krot.err
 LLMREC_PROJ_KROT=1 timeout 400 python bench.py --no-cpu --feat_layout panels > $O/bench_panels_krot.json 2> $O/bench_panels_krot.err
+echo "== one TMA box for W_hi|W_lo (LLMREC_PROJ_WBOX=1)"
+LLMREC_PROJ_WBOX=1 timeout 300 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "projection" > $O/pytest_wbox.log 2>&1; tail -1 $O/pytest_wbox.log
+LLMREC_PROJ_WBOX=1 timeout 400 python bench.py --no-cpu > $O/bench_rows_wbox.json 2> $O/bench_rows_wbox.err
 python - <<'PY'
 import json
-for name in ("rows", "panels", "rows_krot", "panels_krot"):
+for name in ("rows", "panels", "rows_krot", "panels_krot", "rows_wbox"):
     try:
         j = json.loads([l for l in open(f"gpurun_out/next/bench_{name}.json") if l.startswith("{")][0])
         print(name, "ms/step", j["ms_per_step"], "e2e ms", j["e2e"]["ms_per_step"], "families", j["roofline"]["families_ms"], "eval users/s", j.get("eval", {}).get("value"))
