@@ -78,6 +78,22 @@ bool make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t inner, uint64
   return true;
 }
 
+bool make_tmap_3d_f32(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1, uint64_t stride2,
+                      uint32_t b0, uint32_t b1, uint32_t b2) {
+  EncodeFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return false; }
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {stride1, stride2};
+  cuuint32_t box[3] = {b0, b1, b2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (rank 3) failed (%d) dims=%llu,%llu,%llu strides=%llu,%llu box=%u,%u,%u", (int)r,
+                                     (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, (unsigned long long)stride1,
+                                     (unsigned long long)stride2, b0, b1, b2); return false; }
+  return true;
+}
+
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
@@ -577,6 +593,14 @@ int proj_wgrad_tc_group(const llmrec_proj_wgrad_problem* pr, int n_prob, int d, 
       LLMREC_CHECK_ARG(pr[p].k % BK == 0 && (int64_t)(pr[p].k / BK + 4) * npad < (int64_t)INT32_MAX, "proj_wgrad: panel layout needs k %% 32 == 0 and (k/32 + 4)*n < 2^31");
       if (!make_tmap_2d_f32(&P.tmX[p], pr[p].X, (uint64_t)32, (uint64_t)(pr[p].k / 32) * (uint64_t)npad, (uint64_t)128, 32, BK, true)) return 4;
     } else if (!make_tmap_2d_f32(&P.tmX[p], pr[p].X, (uint64_t)pr[p].k, (uint64_t)pr[p].n, (uint64_t)pr[p].ldx * 4, 32, BK, true)) return 4;
+    // experiments (v2 kernel only): one rank-3 box per operand tile instead of 4 + d/32 rank-2 boxes
+    static const bool x3d_env = getenv("LLMREC_PROJ_X3D") != nullptr, g3d_env = getenv("LLMREC_PROJ_G3D") != nullptr;
+    const bool ts = split && d <= 128 && getenv("LLMREC_PROJ_V1") == nullptr;
+    const bool x3d = x3d_env && panel && ts, g3d = g3d_env && ts;
+    if (x3d && !make_tmap_3d_f32(&P.tmX[p], pr[p].X, 32, (uint64_t)npad, (uint64_t)(pr[p].k / 32), 128, (uint64_t)npad * 128, 32, BK, 4)) return 4;
+    if (g3d) {
+      if (!make_tmap_3d_f32(&P.tmG[p], pr[p].dY, 32, (uint64_t)pr[p].n, (uint64_t)(d / 32), (uint64_t)pr[p].lddy * 4, 128, 32, BK, (uint32_t)(d / 32))) return 4;
+    } else
     if (!make_tmap_2d_f32(&P.tmG[p], pr[p].dY, (uint64_t)d, (uint64_t)pr[p].n, (uint64_t)pr[p].lddy * 4, 32, BK, true)) return 4;
     WgProblem& w = P.prob[p];
     w.n = (int)pr[p].n; w.k = pr[p].k; w.ft_tiles = (pr[p].k + BM - 1) / BM;
@@ -584,6 +608,7 @@ int proj_wgrad_tc_group(const llmrec_proj_wgrad_problem* pr, int n_prob, int d, 
     w.chunks = (int)((pr[p].n + w.rows_per_chunk - 1) / w.rows_per_chunk);
     w.item_start = items;
     w.panel = panel ? (int)npad : 0;
+    w.x3d = x3d ? 1 : 0; w.g3d = g3d ? 1 : 0;
     items += w.ft_tiles * w.chunks;
     C.dY[p] = pr[p].dY; C.ld[p] = pr[p].lddy; C.n[p] = pr[p].n; C.db[p] = pr[p].db; C.acc[p] = pr[p].accumulate & LLMREC_WGRAD_ACCUMULATE;
   }

@@ -21,7 +21,8 @@ struct FwdParams {
 };
 
 
-struct WgProblem { int n, k, ft_tiles, chunks, rows_per_chunk, item_start, panel; /* 0 = row-major X, else rows per column panel */ };
+struct WgProblem { int n, k, ft_tiles, chunks, rows_per_chunk, item_start, panel; /* 0 = row-major X, else rows per column panel */
+                   int x3d, g3d; /* experiments: the X tile / the dY tile of a stage arrives as ONE rank-3 TMA box (tmX / tmG are rank-3 maps then) */ };
 struct WgParams {
   CUtensorMap tmX[kMaxProb];
   CUtensorMap tmG[kMaxProb];

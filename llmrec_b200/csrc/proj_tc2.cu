@@ -243,13 +243,19 @@ __global__ void __launch_bounds__(512, 1) proj_wgrad_ts_kernel(const __grid_cons
         mbar_wait(&empty[st.stage], st.phase ^ 1);
         mbar_arrive_expect_tx(&full[st.stage], kTileA + b_bytes);
         const int r = r0 + kb * BK;
+        if (P.prob[p].x3d) {
+          // panels as a rank-3 tensor (32 floats, rows, panels): ONE box = 4 panels x 32 rows, landing as the same four 4 KiB atoms
+          tma_load_3d(sA(st.stage), &P.tmX[p], &full[st.stage], 0, r, ft * 4);
+        } else {
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          // panels: one contiguous 4 KiB run per box; rows past n are the panel's zero padding, panels past k/32 are out of bounds (zero fill)
-          if (P.prob[p].panel) tma_load_2d(sA(st.stage) + a * 4096, &P.tmX[p], &full[st.stage], 0, (ft * 4 + a) * P.prob[p].panel + r);
-          else tma_load_2d(sA(st.stage) + a * 4096, &P.tmX[p], &full[st.stage], ft * BM + a * 32, r);
+          for (int a = 0; a < 4; ++a) {
+            // panels: one contiguous 4 KiB run per box; rows past n are the panel's zero padding, panels past k/32 are out of bounds (zero fill)
+            if (P.prob[p].panel) tma_load_2d(sA(st.stage) + a * 4096, &P.tmX[p], &full[st.stage], 0, (ft * 4 + a) * P.prob[p].panel + r);
+            else tma_load_2d(sA(st.stage) + a * 4096, &P.tmX[p], &full[st.stage], ft * BM + a * 32, r);
+          }
         }
-        for (int b = 0; b < d / 32; ++b) tma_load_2d(sB(st.stage) + b * 4096, &P.tmG[p], &full[st.stage], b * 32, r);
+        if (P.prob[p].g3d) tma_load_3d(sB(st.stage), &P.tmG[p], &full[st.stage], 0, r, 0);   // (32 floats, rows, d/32 column blocks) in one box
+        else for (int b = 0; b < d / 32; ++b) tma_load_2d(sB(st.stage) + b * 4096, &P.tmG[p], &full[st.stage], b * 32, r);
         st.advance();
       }
     }

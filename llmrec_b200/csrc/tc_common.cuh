@@ -55,6 +55,13 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
 // ---- tcgen05 --------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {  // whole warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
@@ -173,5 +180,8 @@ struct TmapKey { const void* base; uint64_t d0, d1, stride; uint32_t b0, b1; uin
 // swizzle32: false -> CU_TENSOR_MAP_SWIZZLE_128B, true -> CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
 bool make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
                       uint32_t box_inner, uint32_t box_outer, bool swizzle32 = false);
+// rank-3 map: dims (d0 contiguous, d1 at stride1 bytes, d2 at stride2 bytes), box (b0, b1, b2); SWIZZLE_128B_ATOM_32B (not cached)
+bool make_tmap_3d_f32(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1, uint64_t stride2,
+                      uint32_t b0, uint32_t b1, uint32_t b2);
 
 }  // namespace llmrec

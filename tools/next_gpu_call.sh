@@ -20,9 +20,15 @@ LLMREC_PROJ_KROT=1 timeout 400 python bench.py --no-cpu --feat_layout panels > $
 echo "== one TMA box for W_hi|W_lo (LLMREC_PROJ_WBOX=1)"
 LLMREC_PROJ_WBOX=1 timeout 300 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "projection" > $O/pytest_wbox.log 2>&1; tail -1 $O/pytest_wbox.log
 LLMREC_PROJ_WBOX=1 timeout 400 python bench.py --no-cpu > $O/bench_rows_wbox.json 2> $O/bench_rows_wbox.err
+echo "== rank-3 TMA boxes in proj_wgrad: X tile (needs panels) / dY tile"
+LLMREC_PROJ_X3D=1 LLMREC_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_experimental_gpu.py -q -m gpu -k "panel_layout_equals" > $O/pytest_x3d.log 2>&1; tail -1 $O/pytest_x3d.log
+LLMREC_PROJ_G3D=1 timeout 300 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "projection" > $O/pytest_g3d.log 2>&1; tail -1 $O/pytest_g3d.log
+LLMREC_PROJ_X3D=1 timeout 400 python bench.py --no-cpu --feat_layout panels > $O/bench_panels_x3d.json 2> $O/bench_panels_x3d.err
+LLMREC_PROJ_G3D=1 timeout 400 python bench.py --no-cpu > $O/bench_rows_g3d.json 2> $O/bench_rows_g3d.err
+LLMREC_PROJ_X3D=1 LLMREC_PROJ_G3D=1 LLMREC_PROJ_WBOX=1 timeout 400 python bench.py --no-cpu --feat_layout panels > $O/bench_panels_all.json 2> $O/bench_panels_all.err
 python - <<'PY'
 import json
-for name in ("rows", "panels", "rows_krot", "panels_krot", "rows_wbox"):
+for name in ("rows", "panels", "rows_krot", "panels_krot", "rows_wbox", "panels_x3d", "rows_g3d", "panels_all"):
     try:
         j = json.loads([l for l in open(f"gpurun_out/next/bench_{name}.json") if l.startswith("{")][0])
         print(name, "ms/step", j["ms_per_step"], "e2e ms", j["e2e"]["ms_per_step"], "families", j["roofline"]["families_ms"], "eval users/s", j.get("eval", {}).get("value"))
