@@ -1,7 +1,7 @@
 #!/bin/bash
 # First GPU call after a round that ended without GPU budget: validates everything that was written on the CPU side and
 # produces the A/B numbers DESIGN.md 7 asks for, all on ONE box (box-to-box variance is +-30 %, only same-call numbers compare).
-#   gpurun --timeout 1500 -- 'bash tools/next_gpu_call.sh'
+#   gpurun --timeout 1800 -- 'bash tools/next_gpu_call.sh'     (about 18 minutes of box time)
 # Outputs land in gpurun_out/next/.
 set -u
 cd "$(dirname "$0")/.."
