@@ -18,6 +18,8 @@ for v in "" "PANELS=1" "LLMREC_PROJ_KROT=1" "PANELS=1 LLMREC_PROJ_KROT=1" "LLMRE
          "PANELS=1 LLMREC_PROJ_X3D=1 LLMREC_PROJ_WBOX=1" "PANELS=1 LLMREC_PROJ_X3D=1 LLMREC_PROJ_WBOX=1 LLMREC_PROJ_KROT=1" "MODE=1" "MODE=1 PANELS=1"; do
   echo "-- ${v:-default}"; env $v timeout 200 python tools/prof_kernels.py proj 2>&1 | tail -2
 done | tee $O/prof_variants.txt
+echo "== netflix-shaped SpMM launches per variant (more gathers in flight / more warps per SM)"
+for v in 0 1 2 3 4; do echo "-- LLMREC_SPMM_VARIANT=$v"; LLMREC_SPMM_VARIANT=$v timeout 200 python tools/prof_kernels.py spmm 2>&1 | grep "tile=0"; done | tee $O/spmm_variants.txt
 echo "== correctness of the variants"
 LLMREC_PROJ_KROT=1 timeout 300 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "projection" 2>&1 | tail -1
 LLMREC_PROJ_WBOX=1 timeout 300 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "projection" 2>&1 | tail -1
