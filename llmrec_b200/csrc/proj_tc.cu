@@ -563,7 +563,8 @@ int proj_fwd_tc_group(const llmrec_proj_fwd_problem* pr, int n_prob, int d, int 
 }
 
 static int wg_rows_per_chunk(int64_t n) {
-  int r = 2048;
+  static const int env = getenv("LLMREC_WG_ROWS") ? atoi(getenv("LLMREC_WG_ROWS")) : 0;   // experiment: rows per work item (multiple of 32)
+  int r = (env >= 256 && env % 32 == 0) ? env : 2048;
   while (r > 256 && n / r < 4) r >>= 1;
   return r;
 }

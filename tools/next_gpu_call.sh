@@ -15,7 +15,7 @@ echo "== bench rows";            timeout 400 python bench.py --no-cpu > $O/bench
 echo "== bench panels";          timeout 400 python bench.py --no-cpu --feat_layout panels > $O/bench_panels.json 2> $O/bench_panels.err; cut -c1-400 $O/bench_panels.json
 echo "== projection kernels alone, every fetch variant (tools/prof_kernels.py proj: ms and GB/s of the grouped fwd / wgrad launches)"
 for v in "" "PANELS=1" "LLMREC_PROJ_KROT=1" "PANELS=1 LLMREC_PROJ_KROT=1" "LLMREC_PROJ_WBOX=1" "PANELS=1 LLMREC_PROJ_X3D=1" "LLMREC_PROJ_G3D=1" \
-         "PANELS=1 LLMREC_PROJ_X3D=1 LLMREC_PROJ_WBOX=1" "PANELS=1 LLMREC_PROJ_X3D=1 LLMREC_PROJ_WBOX=1 LLMREC_PROJ_KROT=1" "MODE=1" "MODE=1 PANELS=1"; do
+         "PANELS=1 LLMREC_PROJ_X3D=1 LLMREC_PROJ_WBOX=1" "PANELS=1 LLMREC_PROJ_X3D=1 LLMREC_PROJ_WBOX=1 LLMREC_PROJ_KROT=1" "MODE=1" "MODE=1 PANELS=1" "LLMREC_WG_ROWS=1024" "LLMREC_WG_ROWS=4096"; do
   echo "-- ${v:-default}"; env $v timeout 200 python tools/prof_kernels.py proj 2>&1 | tail -2
 done | tee $O/prof_variants.txt
 echo "== netflix-shaped SpMM launches per variant (more gathers in flight / more warps per SM)"
