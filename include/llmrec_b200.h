@@ -24,7 +24,7 @@ extern "C" {
 
 typedef void* llmrec_stream_t; /* cudaStream_t */
 
-#define LLMREC_ABI_VERSION 1
+#define LLMREC_ABI_VERSION 2
 #define LLMREC_MAX_SEG 16
 
 int llmrec_abi_version(void);
@@ -164,6 +164,10 @@ int llmrec_fuse_bwd_f32(const float* g, int64_t ldg, int32_t n_layers, float* d_
  * out_host-visible results live in `out` (device, 4 floats per head: mf, emb, kept, _) .
  * idx are int32 device arrays of length B.  `n_keep` = int((1-drop_rate)*B) computed by the caller
  * in double arithmetic like the reference (main.py:161-162).
+ * `meta` (may be NULL): DEVICE int32[2] = {live B', n_keep}.  When given, B is only the CAPACITY the launch is sized
+ * for (index arrays and `work` hold B entries) and the kernels read the live length and n_keep from `meta` -- one
+ * captured CUDA graph then serves every batch length <= B (the augmented-edge filter makes B' vary per step).
+ * Two launches: score + per-head radix select of the kept set (ties -> lower position) + loss; scatter of row gradients.
  * --------------------------------------------------------------------------------------------- */
 typedef struct {
   const float* XU; const float* XI;
@@ -174,10 +178,23 @@ typedef struct {
 
 int llmrec_bpr_heads_f32(const llmrec_bpr_head* heads_host, int32_t n_heads,
                          const int32_t* users, const int32_t* pos, const int32_t* neg, int32_t B,
-                         int32_t n_keep, float regs0_over_bs, int32_t d,
+                         int32_t n_keep, const int32_t* meta, float regs0_over_bs, int32_t d,
                          float* out /* [n_heads*4] */, float* loss_accum /* [1], += */,
                          float* work /* llmrec_bpr_work_elems() floats, zeroed once */, llmrec_stream_t stream);
 int64_t llmrec_bpr_work_elems(int32_t n_heads, int32_t B);
+
+/* First touch of every gradient buffer of a step, one launch instead of a memset per buffer: region r is written
+ * G_r[n x width] = X_r ? c_r * X_r : 0, and *loss = sum_r 0.5 * c_r * sum(X_r^2) (OVERWRITTEN: this is the first term of
+ * the step's loss) -- feat_reg_loss_calculation (main.py:151-156) and its gradient for the regions with X, plain zeroing
+ * for the buffers the BPR heads scatter-add into.  <= 16 regions (128-bit accesses when width / ld % 4 == 0 and aligned).
+ * scratch: llmrec_grad_init_scratch() floats, zeroed once by the caller (the kernel leaves its ticket at zero). */
+typedef struct {
+  float* G; const float* X;
+  int64_t ldg, ldx, n;
+  int32_t width; float c;
+} llmrec_grad_region;
+int llmrec_grad_init_f32(const llmrec_grad_region* regions_host, int32_t n_regions, float* loss, float* scratch, llmrec_stream_t stream);
+int64_t llmrec_grad_init_scratch(void);
 
 /* feat_reg_loss_calculation (main.py:151-156): loss += c * 0.5*sum(X^2) ; G = (accumulate? G:0) + c*X.
  * G may be NULL (loss only). */

@@ -102,6 +102,8 @@ class MM_Model(nn.Module):
         key = (id(ui_graph), id(iu_graph), self.user_id_embedding.weight.data_ptr())
         if self._hp is None or self._hp_key != key:
             args = get_args()
+            if getattr(args, "hoist_side", 0):
+                raise NotImplementedError("--hoist_side 1 is not wired in this build")
             if not _on_device(self.user_id_embedding.weight):
                 raise RuntimeError("MM_Model runs on the B200 kernels only: move it to CUDA first (no CPU path)")
             ui_f, ui_b = operators_from_coo(ui_graph)

@@ -44,6 +44,11 @@ class BprHead(C.Structure):
                 ("w_mf", C.c_float), ("w_emb", C.c_float)]
 
 
+class GradRegion(C.Structure):
+    _fields_ = [("G", C.c_void_p), ("X", C.c_void_p), ("ldg", C.c_int64), ("ldx", C.c_int64), ("n", C.c_int64),
+                ("width", C.c_int32), ("c", C.c_float)]
+
+
 # name -> (restype, argtypes); must list every symbol of include/llmrec_b200.h (checked by tests)
 SIGNATURES = {
     "llmrec_abi_version": (C.c_int, []),
@@ -66,7 +71,9 @@ SIGNATURES = {
     "llmrec_fuse_bwd_f32": (C.c_int, [c_f32p, C.c_int64, C.c_int32, c_f32p, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
                                       C.POINTER(C.c_float), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int32, C.c_int32,
                                       c_i32p, C.c_int64, C.c_int32, c_stream]),
-    "llmrec_bpr_heads_f32": (C.c_int, [C.POINTER(BprHead), C.c_int32, c_i32p, c_i32p, c_i32p, C.c_int32, C.c_int32, C.c_float,
+    "llmrec_grad_init_f32": (C.c_int, [C.POINTER(GradRegion), C.c_int32, c_f32p, c_f32p, c_stream]),
+    "llmrec_grad_init_scratch": (C.c_int64, []),
+    "llmrec_bpr_heads_f32": (C.c_int, [C.POINTER(BprHead), C.c_int32, c_i32p, c_i32p, c_i32p, C.c_int32, C.c_int32, c_i32p, C.c_float,
                                        C.c_int32, c_f32p, c_f32p, c_f32p, c_stream]),
     "llmrec_bpr_work_elems": (C.c_int64, [C.c_int32, C.c_int32]),
     "llmrec_sqnorm_grad_f32": (C.c_int, [c_f32p, C.c_int64, c_f32p, C.c_int64, C.c_int64, C.c_int32, C.c_float, C.c_int32,

@@ -98,7 +98,7 @@ class ShardedHotPath:
     """ID-only training step over a ShardedGraph; world size 1 reproduces engine.HotPath(feats=None) exactly."""
 
     def __init__(self, graph: ShardedGraph, E_u_local: torch.Tensor, E_i: torch.Tensor, cfg: HotPathConfig, user_lo: int, group=None, solo=False,
-                 item_sharded: bool = False):
+                 item_sharded: bool = False, demand: bool = False):
         """item_sharded (opt-in, needs n_items % world == 0): the item-side exchanges whose result is only consumed row-wise
         become reduce-scatter -> row-local work on this rank's item range -> all-gather (same bytes on NVLink as the
         all-reduce): the scale/softmax after each forward exchange runs on 1/world of the rows, and the item table's AdamW
@@ -132,6 +132,7 @@ class ShardedHotPath:
         else:
             self.opt = ops.AdamW([E_u_local, E_i], lr=1e-4)
         self.comm_bytes = 0
+        self.demand = False
 
     def set_lr(self, lr):
         self.opt.lr = lr

@@ -110,7 +110,7 @@ class HotPath:
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
         self.n_heads = (3 + len(self.keys)) if self.has_feats else 1
         self.head_out = torch.zeros(self.n_heads * 4, dtype=torch.float32, device=dev)
-        self._bpr_work = None
+        self._bpr_work, self._cap, self._graph = None, 0, None
         self.opt = None
         self.timer = None
 
@@ -255,76 +255,112 @@ class HotPath:
                 ops.proj_wgrad_group(probs, d, m)
 
     # ---- losses + their gradients w.r.t. the forward outputs ---------------------------------------------
-    def loss_and_output_grads(self, users, pos, neg):
-        """users/pos/neg: int32 CUDA tensors of equal length B' (sampled + augmented triplets)."""
+    def ensure_capacity(self, cap):
+        """Index buffer [4 x cap] (rows users, pos, neg, meta = {B', n_keep}), the per-B' meta table and the BPR work block,
+        sized ONCE for a batch capacity: every captured graph reads these addresses, so they are only ever replaced together
+        with the graphs (a per-B' work buffer freed under a live graph was a use-after-free)."""
+        if getattr(self, "_cap", 0) >= cap:
+            return
+        dev = self.E_u.device
+        if getattr(self, "_graph", None) is not None:
+            torch.cuda.synchronize()
+        self._graph = None
+        self._cap = int(cap)
+        self._gidx = torch.zeros((4, self._cap), dtype=torch.int32, device=dev)
+        keep = [int((1 - self.cfg.prune_loss_drop_rate) * b) for b in range(self._cap + 1)]      # main.py:161-162 (double arithmetic)
+        self._meta_table = torch.tensor([[b, k] for b, k in enumerate(keep)], dtype=torch.int32).to(dev)
+        self._bpr_work = ops.bpr_work(self.n_heads, self._cap, dev)
+
+    def loss_and_output_grads(self, users, pos, neg, meta=None):
+        """users/pos/neg: int32 CUDA tensors of equal length B' (sampled + augmented triplets) -- or, with `meta` (int32 CUDA
+        {B', n_keep}), capacity-sized buffers whose first B' entries are live (the CUDA-graph path)."""
         c = self.cfg
         B = int(users.numel())
+        self.ensure_capacity(max(B, 2 * c.batch_size))
         n_keep = int((1 - c.prune_loss_drop_rate) * B)                     # main.py:161-162 (double arithmetic)
-        if self._bpr_work is None or self._bpr_work[0] != B:
-            self._bpr_work = (B, ops.bpr_work(self.n_heads, B, users.device))
-        with self._t("memset"):
-            self.loss.zero_()
-            self.gU.zero_(); self.gI.zero_()
-            if self.has_feats:
-                self.GFu.zero_(); self.GFi.zero_(); self.Gprof_u.zero_(); self.Gprof_i.zero_()
         heads = [(self.U, self.I, self.gU, self.gI, 1.0, 1.0)]                                                        # main.py:232-235
+        regions = [(self.gU, None, 0.0), (self.gI, None, 0.0)]
         if self.has_feats:
             creg = c.feat_reg_decay / self.ni                                                                          # main.py:151-156
             d2 = 2 * self.d
-            with self._t("feat_reg"):
-                ops.sqnorm_grad(self.Fu[:, :d2], self.GFu[:, :d2], creg, False, self.loss)
-                ops.sqnorm_grad(self.Fi[:, :d2], self.GFi[:, :d2], creg, False, self.loss)
+            # first touch of the gradient buffers: feat_reg gradient c*X on the image/text blocks (its value starts the loss), zeros elsewhere
+            regions += [(self.GFu[:, :d2], self.Fu[:, :d2], creg), (self.GFi[:, :d2], self.Fi[:, :d2], creg),
+                        (self.Gprof_u, None, 0.0), (self.Gprof_i, None, 0.0)]
+            if self.S > 2:
+                regions += [(self.GFu[:, d2:], None, 0.0), (self.GFi[:, d2:], None, 0.0)]
             heads.append((self.blk(self.Fu, 0), self.blk(self.Fi, 0), self.blk(self.GFu, 0), self.blk(self.GFi, 0), c.mm_mf_rate, 0.0))  # :238-241
             heads.append((self.blk(self.Fu, 1), self.blk(self.Fi, 1), self.blk(self.GFu, 1), self.blk(self.GFi, 1), c.mm_mf_rate, 0.0))  # :242-246
             for j in range(len(self.keys)):                                                                            # :248-254
                 heads.append((self.prof_u, self.blk(self.Fi, 2 + j), self.Gprof_u, self.blk(self.GFi, 2 + j), c.aug_mf_rate, 0.0))
+        with self._t("grad_init"):
+            ops.grad_init(regions, self.loss)
         with self._t("bpr"):
-            ops.bpr_heads(heads, users, pos, neg, n_keep, c.regs0 / c.batch_size, self.head_out, self.loss, self._bpr_work[1])
+            ops.bpr_heads(heads, users, pos, neg, n_keep, c.regs0 / c.batch_size, self.head_out, self.loss, self._bpr_work, meta=meta)
         return self.loss
 
-    def train_step(self, users, pos, neg):
+    def train_step(self, users, pos, neg, meta=None):
         """forward + losses + backward + AdamW; everything stays on the current stream."""
         if self.opt is None:
             raise RuntimeError("attach an optimizer with set_optimizer() first")
         self.forward()
-        self.loss_and_output_grads(users, pos, neg)
+        self.loss_and_output_grads(users, pos, neg, meta)
         self.backward()
         with self._t("adamw"):
             self.opt.step([self.grads[k] for k in self._opt_names])
         return self.loss
 
+    def families(self, users, pos, neg):
+        """name -> thunk launching one kernel family of the step (bench.py times each from its own CUDA graph)."""
+        f = {"spmm_fwd": self._prop_fwd, "fuse_fwd": self._fuse_fwd, "loss_heads": lambda: self.loss_and_output_grads(users, pos, neg),
+             "fuse_bwd": self._fuse_bwd, "spmm_bwd": self._chain_bwd, "adamw": lambda: self.opt.step([self.grads[k] for k in self._opt_names])}
+        if self.has_feats:
+            f.update(proj_fwd=self._proj_fwd, proj_wgrad=self._wgrad)
+        return f
+
     # ---- CUDA-graph replay of the whole step -----------------------------------------------------------
-    def train_step_graphed(self, users, pos, neg):
-        """Same as train_step, replayed from a CUDA graph captured per batch length B' (the ~45 launches
-        of a step cost more host time than device time at netflix scale).  users/pos/neg: int32 CUDA
-        tensors; they are copied into static index buffers the graph reads."""
-        B = int(users.numel())
-        if not hasattr(self, "_graphs"):
-            self._graphs, self._gidx = {}, None
-        if self._gidx is None or self._gidx.shape[1] < B:
-            self._gidx = torch.zeros((3, max(B, 2 * self.cfg.batch_size)), dtype=torch.int32, device=users.device)
-            self._graphs.clear()
-        self._gidx[0, :B].copy_(users, non_blocking=True)
-        self._gidx[1, :B].copy_(pos, non_blocking=True)
-        self._gidx[2, :B].copy_(neg, non_blocking=True)
-        g = self._graphs.get(B)
-        if g is None:
-            u, p, n = self._gidx[0, :B], self._gidx[1, :B], self._gidx[2, :B]
+    def index_buffer(self, need):
+        """The static [4 x cap] int32 buffer the captured step reads: rows users / pos / neg, row 3 = {B', n_keep, ...}."""
+        self.ensure_capacity(max(int(need), 2 * self.cfg.batch_size))
+        return self._gidx
+
+    def meta_row(self, B):
+        """(B', n_keep) for the host side of a staging buffer (same double arithmetic as main.py:161-162)."""
+        return int(B), int((1 - self.cfg.prune_loss_drop_rate) * B)
+
+    def replay_staged(self):
+        """Replay the captured step on whatever the index buffer holds (Trainer copies a pinned staging slot straight into it).
+        ONE graph serves every batch length: the kernels take B' and n_keep from row 3 of the buffer."""
+        if getattr(self, "_graph", None) is None:
+            cap = self._cap
+            u, p, n, meta = self._gidx[0], self._gidx[1], self._gidx[2], self._gidx[3]
+            torch.cuda.synchronize()
+            held = self._gidx.clone()
             if not getattr(self, "_warm", False):
-                # one eager step sizes every lazily allocated scratch buffer; its parameter update is undone
+                # one eager step at full capacity sizes every lazily allocated scratch buffer; its parameter update is undone
                 snap = self._snapshot_state()
-                self.train_step(u, p, n)
+                self._gidx[3, :2].copy_(self._meta_table[cap])
+                self.train_step(u, p, n, meta)
                 self._restore_state(snap)
+                self._gidx.copy_(held)
                 self._warm = True
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            snap = self._snapshot_state()
             with torch.cuda.graph(g):
-                self.train_step(u, p, n)
-            self._restore_state(snap)        # capture does not execute, but keep state handling symmetric
-            self._graphs[B] = g
-        g.replay()
+                self.train_step(u, p, n, meta)
+            self._graph = g
+        self._graph.replay()
         return self.loss
+
+    def train_step_graphed(self, users, pos, neg):
+        """Same as train_step, replayed from the CUDA graph (the ~40 launches of a step cost more host time than device time at
+        netflix scale).  users/pos/neg: int32 CUDA tensors of length B'; they are copied into the static index buffer."""
+        B = int(users.numel())
+        gi = self.index_buffer(B)
+        gi[0, :B].copy_(users, non_blocking=True)
+        gi[1, :B].copy_(pos, non_blocking=True)
+        gi[2, :B].copy_(neg, non_blocking=True)
+        gi[3, :2].copy_(self._meta_table[B], non_blocking=True)
+        return self.replay_staged()
 
     def _snapshot_state(self):
         o = self.opt

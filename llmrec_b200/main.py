@@ -46,11 +46,12 @@ def set_seed(seed):
 
 
 class _StagingSlot:
-    """One pinned [3 x cap] int32 index buffer + the event recorded after its H2D copy.  A slot is rewritten only after
-    that copy has completed, so the host may run ahead of the device by at most the ring length."""
+    """One pinned [4 x cap] int32 index buffer (rows users / pos / neg / meta = {B', n_keep}) + the event recorded after its
+    H2D copy.  A slot is rewritten only after that copy has completed, so the host may run ahead of the device by at most the
+    ring length."""
 
     def __init__(self, cap):
-        self.host = torch.empty((3, cap), dtype=torch.int32).pin_memory()
+        self.host = torch.zeros((4, cap), dtype=torch.int32).pin_memory()
         self.np = self.host.numpy()
         self.event = torch.cuda.Event()
 
@@ -196,13 +197,14 @@ class Trainer(object):
         return users, pos_items, neg_items
 
     def _next_slot(self, need):
-        """Next pinned staging slot of the ring (4 slots), free to be rewritten."""
-        cap = max(need, 2 * self.batch_size + 8)
-        if not self._slots or self._slots[0].host.shape[1] < cap:
+        """Next pinned staging slot of the ring (4 slots), free to be rewritten.  The device side of the copy is the engine's
+        static index buffer (what the captured CUDA graph reads), so a batch crosses PCIe exactly once."""
+        self._idx_dev = self.hot.index_buffer(max(need, 2 * self.batch_size + 8))
+        cap = self._idx_dev.shape[1]
+        if not self._slots or self._slots[0].host.shape[1] != cap:
             if self._slots:
                 torch.cuda.synchronize()                                  # copies out of the old ring may still be in flight
             self._slots = [_StagingSlot(cap) for _ in range(4)]
-            self._idx_dev = torch.empty((3, cap), dtype=torch.int32, device=self.device)
             self._slot_i = 0
         slot = self._slots[self._slot_i]
         self._slot_i = (self._slot_i + 1) % len(self._slots)
@@ -210,8 +212,11 @@ class Trainer(object):
         return slot
 
     def _push(self, slot, B):
-        self._idx_dev[:, :B].copy_(slot.host[:, :B], non_blocking=True)
+        slot.np[3, 0:2] = self.hot.meta_row(B)                            # {B', n_keep}: the graph's kernels read them from the device
+        w = max(B, 2)
+        self._idx_dev[:, :w].copy_(slot.host[:, :w], non_blocking=True)
         slot.event.record()
+        self.last_h2d_bytes = 4 * 4 * w
         d = self._idx_dev
         return d[0, :B], d[1, :B], d[2, :B]
 
@@ -230,12 +235,13 @@ class Trainer(object):
         if self._batch_sampler is None:
             return self.upload_batch(*self.sample_batch())
         slot = self._next_slot(2 * self._batch_sampler.batch)
-        B = self._batch_sampler.draw(slot.np, self.args.aug_sample_rate)
+        B = self._batch_sampler.draw(slot.np[:3], self.args.aug_sample_rate)
         self.new_batch_size = B - self._batch_sampler.batch
         return self._push(slot, B)
 
     def _step(self, u, p, n):
-        loss = self.hot.train_step_graphed(u, p, n) if self.use_graph else self.hot.train_step(u, p, n)
+        # u, p, n are views of the engine's index buffer (see _push): the graph replays on what was just staged
+        loss = self.hot.replay_staged() if self.use_graph else self.hot.train_step(u, p, n)
         # device-side epoch accumulators: [total, mf(main), emb(main)]
         self._epoch_stats[0:1] += loss
         self._epoch_stats[1:3] += self.hot.head_out[0:2]

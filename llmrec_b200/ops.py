@@ -92,6 +92,8 @@ class CsrOperator:
         k = self.plan
         need = k.n_split_tiles * width
         if need and (k.scratch is None or k.scratch.numel() < need):
+            if k.scratch is not None:
+                _retired.append(k.scratch)
             k.scratch = torch.empty(need, dtype=torch.float32, device=self.rowptr.device)
         return N.SpmmTiling(_p(k.tiles), _p(k.split_row), _p(k.split_first), _p(k.scratch), k.n_tiles, k.n_split, k.n_split_tiles, 0)
 
@@ -134,9 +136,14 @@ PROJ_MODE = {"3xtf32": 0, "tf32": 1, "fp32": 2}
 _scratch = {}
 
 
+_retired = []     # outgrown scratch buffers stay allocated: a captured CUDA graph may still hold their addresses
+
+
 def _get_scratch(key, n, device):
     t = _scratch.get(key)
     if t is None or t.numel() < n:
+        if t is not None:
+            _retired.append(t)
         t = _scratch[key] = torch.empty(max(int(n), 1), dtype=torch.float32, device=device)
     return t
 
@@ -254,8 +261,9 @@ def bpr_work(n_heads, B, device):
     return torch.zeros(int(N.lib().llmrec_bpr_work_elems(n_heads, B)), dtype=torch.float32, device=device)
 
 
-def bpr_heads(heads, users, pos, neg, n_keep, regs0_over_bs, out, loss, work):
-    """heads: list of (XU, XI, GU|None, GI|None, w_mf, w_emb).  See include/llmrec_b200.h."""
+def bpr_heads(heads, users, pos, neg, n_keep, regs0_over_bs, out, loss, work, meta=None):
+    """heads: list of (XU, XI, GU|None, GI|None, w_mf, w_emb).  See include/llmrec_b200.h.
+    meta: optional int32 CUDA tensor {live B', n_keep}; users/pos/neg/work are then sized for the capacity B."""
     arr = (N.BprHead * len(heads))()
     d = int(heads[0][0].shape[1])
     for i, (XU, XI, GU, GI, wmf, wemb) in enumerate(heads):
@@ -263,9 +271,30 @@ def bpr_heads(heads, users, pos, neg, n_keep, regs0_over_bs, out, loss, work):
         arr[i] = N.BprHead(_p(XU), _p(XI), _p(GU), _p(GI), _ld(XU), _ld(XI), _ld(GU) if GU is not None else 0,
                            _ld(GI) if GI is not None else 0, float(wmf), float(wemb))
     B = int(users.numel())
-    N.check(N.lib().llmrec_bpr_heads_f32(arr, len(heads), _p(_i32(users)), _p(_i32(pos)), _p(_i32(neg)), B, int(n_keep),
+    if work.numel() < N.lib().llmrec_bpr_work_elems(len(heads), B):
+        raise ValueError("bpr_heads: work buffer too small for this capacity")
+    N.check(N.lib().llmrec_bpr_heads_f32(arr, len(heads), _p(_i32(users)), _p(_i32(pos)), _p(_i32(neg)), B, int(n_keep), _p(meta),
                                           float(regs0_over_bs), d, _p(out), _p(loss), _p(work), _stream()), "bpr_heads")
-    _count(4)
+    _count(2)
+
+
+_ginit = {}
+
+
+def grad_init(regions, loss):
+    """regions: list of (G, X|None, c): G = c*X (or 0) written once; loss = sum 0.5*c*|X|^2 (overwritten).  One launch."""
+    arr = (N.GradRegion * len(regions))()
+    for i, (G, X, c) in enumerate(regions):
+        _mat(G)
+        if X is not None and tuple(_mat(X).shape) != tuple(G.shape):
+            raise ValueError("grad_init: X and G shapes differ")
+        arr[i] = N.GradRegion(_p(G), _p(X), _ld(G), _ld(X) if X is not None else 0, G.shape[0], G.shape[1], float(c))
+    key = loss.device.index
+    sc = _ginit.get(key)
+    if sc is None:
+        sc = _ginit[key] = torch.zeros(int(N.lib().llmrec_grad_init_scratch()), dtype=torch.float32, device=loss.device)
+    N.check(N.lib().llmrec_grad_init_f32(arr, len(regions), _p(loss), _p(sc), _stream()), "grad_init")
+    _count()
 
 
 _partial = {}
@@ -317,6 +346,8 @@ def score_topk(U, I, users, mask_rowptr, mask_col, K, mode=0, want_vals=False):
     key = U.device.index
     scratch = _score_scratch.get(key)
     if need and (scratch is None or scratch.numel() < need):
+        if scratch is not None:
+            _retired.append(scratch)
         scratch = _score_scratch[key] = torch.empty(need, dtype=torch.float32, device=U.device)
     N.check(N.lib().llmrec_score_topk_f32(_p(U), _ld(U), _p(I), _ld(I), _p(_i32(users)), nb, ni, d, _p(mask_rowptr), _p(mask_col), K,
                                            _p(idx), _p(val), mode, _p(scratch), scratch.numel() if scratch is not None else 0,

@@ -76,6 +76,10 @@ _EXTRA = [
     ("feat_layout", dict(default="rows", choices=["rows", "panels"], help="HBM layout of the constant side-feature tables: row-major, or 32-column panels (contiguous tiles for the projection kernels)")),
     ("cuda_graph", dict(type=int, default=1, help="replay the training step from a CUDA graph (1) or launch eagerly (0)")),
     ("host_sampler", dict(default="native", choices=["native", "python"], help="bit-identical C sampler or the reference's Python loops")),
+    ("hoist_side", dict(type=int, default=0, help="1: precompute the propagation of the constant side features once (ui.X, iu.ui.X) and project only the "
+                                                   "batch's rows per step (SURVEY.md 8f-3); same results within the golden tolerances; off automatically "
+                                                   "when drop_rate > 0 or the mask branch is on")),
+    ("device_sampler", dict(type=int, default=0, help="1: draw the batches on the GPU (non-parity RNG stream, SURVEY.md 8f-1); 0 replays the reference's host sampling")),
 ]
 
 DATASET_ALIASES = {"netflix": "netflix_valid_item", "movielens": "preprocessed_raw_MovieLens", "movieLens": "preprocessed_raw_MovieLens"}

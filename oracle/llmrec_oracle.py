@@ -227,8 +227,10 @@ def num_remember(n: int, drop_rate: float) -> int:
 
 
 def prune_mean(pred: torch.Tensor, drop_rate: float) -> torch.Tensor:
-    """Mean of the num_remember smallest entries (ascending argsort; main.py:158-165)."""
-    order = torch.argsort(pred.detach(), stable=True)
+    """Mean of the num_remember smallest entries (ascending argsort; main.py:158-165).  The reference sorts on the HOST
+    (`np.argsort(pred.cpu().data).cuda()`, main.py:159): with device tensors that is a D2H copy + CPU sort + H2D per head,
+    reproduced here so the torch-on-GPU baseline leg pays what the reference pays."""
+    order = torch.argsort(pred.detach().cpu(), stable=True).to(pred.device)
     keep = order[:num_remember(pred.shape[0], drop_rate)]
     return pred[keep].mean()
 
@@ -345,7 +347,7 @@ def evaluate(U, I, data: OracleData, users, cfg: OracleConfig, is_val=False, fai
     tops = {}
     for s in range(0, n, step):
         blk = users[s:s + step]
-        rate = torch.matmul(U[blk], I.t()).detach().numpy()
+        rate = torch.matmul(U[blk], I.t()).detach().cpu().numpy()                # batch_test.py:150-154
         if faithful:
             lists = [rank_user_heapq(rate[j], data.train_items.get(u, []), data.n_items, kmax) for j, u in enumerate(blk)]
         else:
@@ -368,13 +370,16 @@ def set_seed(seed):
 
 
 class OracleTrainer:
-    def __init__(self, data: OracleData, cfg: OracleConfig):
+    def __init__(self, data: OracleData, cfg: OracleConfig, device="cpu"):
+        """device="cuda" runs the SAME torch ops through cuSPARSE / cuBLAS / ATen (the "reference torch.sparse on the same
+        B200" baseline of BASELINE.json configs[1]; the reference builds on CPU and calls .cuda(), main.py:91,96)."""
         self.data, self.cfg = data, cfg
-        self.ui, self.iu = build_graphs(data.train_mat)
-        self.params = init_params(cfg, data)
-        self.feats = dict(image=torch.tensor(data.image_feats).float(), text=torch.tensor(data.text_feats).float(),
-                          user=torch.tensor(data.user_feats).float(),
-                          item={k: torch.tensor(v).float() for k, v in data.item_feats.items()})
+        dev = self.device = torch.device(device)
+        self.ui, self.iu = (g.to(dev) for g in build_graphs(data.train_mat))
+        self.params = {k: v.detach().to(dev).requires_grad_(True) for k, v in init_params(cfg, data).items()}
+        self.feats = dict(image=torch.tensor(data.image_feats).float().to(dev), text=torch.tensor(data.text_feats).float().to(dev),
+                          user=torch.tensor(data.user_feats).float().to(dev),
+                          item={k: torch.tensor(v).float().to(dev) for k, v in data.item_feats.items()})
         # torch default AdamW: betas (0.9, 0.999), eps 1e-8, weight_decay 0.01 (main.py:100-104)
         self.opt = torch.optim.AdamW(list(self.params.values()), lr=cfg.lr)
 

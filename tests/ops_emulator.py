@@ -109,7 +109,20 @@ def bpr_work(n_heads, B, device):
     return torch.zeros(1)
 
 
-def bpr_heads(heads, users, pos, neg, n_keep, regs0_over_bs, out, loss, work):      # llmrec_bpr_heads_f32
+def grad_init(regions, loss):                            # llmrec_grad_init_f32
+    loss.zero_()
+    for G, X, c in regions:
+        if X is None:
+            G.zero_()
+        else:
+            G.copy_(c * X)
+            loss += c * 0.5 * X.pow(2).sum()
+
+
+def bpr_heads(heads, users, pos, neg, n_keep, regs0_over_bs, out, loss, work, meta=None):      # llmrec_bpr_heads_f32
+    if meta is not None:                                 # capacity-sized index buffers: the live length and n_keep come from `meta`
+        B, n_keep = int(meta[0]), int(meta[1])
+        users, pos, neg = users[:B], pos[:B], neg[:B]
     u, p, n = users.long(), pos.long(), neg.long()
     for h, (XU, XI, GU, GI, w_mf, w_emb) in enumerate(heads):
         a = XU[u].clone().requires_grad_(True)
@@ -179,7 +192,7 @@ def install():
     me = sys.modules[__name__]
     import llmrec_b200.graph as G
     for name in ("CsrOperator", "row_scale_softmax", "row_softmax_bwd", "fuse_fwd", "fuse_bwd", "gather_rows", "scatter_add_rows",
-                 "bpr_work", "bpr_heads", "AdamW", "proj_fwd_group", "proj_wgrad_group", "sqnorm_grad", "score_topk", "topk_hits"):
+                 "bpr_work", "bpr_heads", "grad_init", "AdamW", "proj_fwd_group", "proj_wgrad_group", "sqnorm_grad", "score_topk", "topk_hits"):
         setattr(ops, name, getattr(me, name))
     D.CsrOperator = CsrOperator
     G.CsrOperator = CsrOperator

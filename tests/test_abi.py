@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), f"{n} declared in include/llmrec_b200.h but not exported"
     assert set(names) == set(_native.SIGNATURES), set(names) ^ set(_native.SIGNATURES)
     lib.llmrec_abi_version.restype = ctypes.c_int
-    assert lib.llmrec_abi_version() == 1
+    assert lib.llmrec_abi_version() == 2
 
 
 def test_no_device_means_loud_failure():

@@ -319,3 +319,56 @@ def test_topk_hits():
     users = torch.tensor([2, 0], dtype=torch.int32, device=cuda)
     rowptr = torch.tensor([0, 1, 1, 3], dtype=torch.int32, device=cuda); col = torch.tensor([2, 9, 5], dtype=torch.int32, device=cuda)
     assert ops.topk_hits(idx, users, rowptr, col).cpu().tolist() == [[1, 0, 1], [0, 1, 0]]
+
+
+@pytest.mark.parametrize("B,n_keep", [(1, 0), (1, 1), (7, 7), (1126, 326), (5000, 1450), (40000, 11600)])
+def test_bpr_select_large_batches_with_ties_and_device_meta(B, n_keep):
+    """The per-head radix select against torch's stable argsort: heavy ties (scores drawn from 5 values), the kept set must be the
+    n_keep smallest log-sigmoids with ties -> lower position; the same call again with capacity > B and {B, n_keep} read from
+    the device (`meta`, the CUDA-graph path) must give the same kept set and loss."""
+    from llmrec_b200 import ops
+    g = torch.Generator().manual_seed(B)
+    d, nu, ni = 16, 50, 60
+    XU = torch.zeros(nu, d); XU[:, 0] = 1.0
+    XI = torch.zeros(ni, d); XI[:, 0] = torch.randint(-2, 3, (ni,), generator=g).float()      # 5 distinct scores -> massive ties
+    users = torch.randint(0, nu, (B,), generator=g, dtype=torch.int32)
+    pos = torch.randint(0, ni, (B,), generator=g, dtype=torch.int32)
+    neg = torch.randint(0, ni, (B,), generator=g, dtype=torch.int32)
+    x = XI[pos.long(), 0] - XI[neg.long(), 0] + 1e-8
+    maxi = torch.nn.functional.logsigmoid(x)
+    keep = torch.argsort(maxi, stable=True)[:n_keep]
+    want = -(maxi[keep].double().mean()) if n_keep else float("nan")
+    for cap in (B, B + 37):
+        pad = lambda t: torch.cat([t, torch.zeros(cap - B, dtype=torch.int32)]).to(cuda)
+        meta = torch.tensor([B, n_keep], dtype=torch.int32, device=cuda) if cap != B else None
+        GU, GI = torch.zeros(nu, d, device=cuda), torch.zeros(ni, d, device=cuda)
+        out = torch.zeros(4, device=cuda); loss = torch.zeros(1, device=cuda)
+        work = ops.bpr_work(1, cap, cuda)
+        for _ in range(2):
+            ops.bpr_heads([(XU.to(cuda), XI.to(cuda), GU, GI, 1.0, 0.0)], pad(users), pad(pos), pad(neg), n_keep, 0.0, out, loss, work, meta=meta)
+        torch.cuda.synchronize()
+        kept = work[32 + 6 * cap: 32 + 6 * cap + B].cpu()                 # keep flags of head 0 (work layout in csrc/bpr.cu)
+        ref = torch.zeros(B); ref[keep] = 1.0
+        assert torch.equal(kept, ref), (cap, int((kept != ref).sum()))
+        if n_keep:
+            assert abs(float(out[0]) - float(want)) <= 2e-6 * max(1.0, abs(float(want)))
+        else:
+            assert bool(torch.isnan(out[0]))
+
+
+def test_grad_init_regions():
+    from llmrec_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    wide = torch.randn(777, 7 * 64, generator=g).to(cuda)
+    G = torch.full((777, 7 * 64), 5.0, device=cuda)
+    odd = torch.full((50, 13), 3.0, device=cuda)                            # width % 4 != 0: scalar path of the same kernel
+    oddX = torch.randn(50, 13, generator=g).to(cuda)
+    loss = torch.full((1,), 123.0, device=cuda)
+    c = 2.5e-3
+    for _ in range(2):                                                       # second call: the ticket was left at zero
+        ops.grad_init([(G[:, :128], wide[:, :128], c), (G[:, 128:], None, 0.0), (odd, oddX, 0.5)], loss)
+    torch.testing.assert_close(G[:, :128], c * wide[:, :128], rtol=1e-6, atol=1e-9)
+    assert float(G[:, 128:].abs().sum()) == 0.0
+    torch.testing.assert_close(odd, 0.5 * oddX, rtol=1e-6, atol=1e-9)
+    want = c * 0.5 * float((wide[:, :128].double() ** 2).sum()) + 0.5 * 0.5 * float((oddX.double() ** 2).sum())
+    assert abs(float(loss) - want) <= 1e-5 * want                            # overwritten, not accumulated

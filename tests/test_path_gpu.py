@@ -204,3 +204,30 @@ def test_movielens_config_d128_L3_vs_oracle(tmp_path):
     ores, _ = otr.test()
     for k in ("recall", "ndcg", "precision", "hit_ratio"):
         np.testing.assert_allclose(res[k], ores[k], atol=1e-4)
+
+
+def test_graphed_steps_with_varying_batch_length_match_eager(tiny_root):
+    """ONE captured graph serves every batch length (B' and n_keep come from the device): alternate two lengths over many steps,
+    allocate and free memory in between (a per-B' scratch buffer freed under a live graph was a use-after-free) and
+    hold the result to the eager path on identical batches."""
+    trg, gen, M = _trainer(tiny_root, ["--cuda_graph", "1"])
+    tre, _, _ = _trainer(tiny_root, ["--cuda_graph", "0"])
+    M.set_seed(11)
+    batches = [trg.sample_batch() for _ in range(14)]
+    junk = []
+    for i, (u, p, n) in enumerate(batches):
+        B = len(u) if i % 2 == 0 else len(u) - 9 - (i % 5)
+        u, p, n = u[:B], p[:B], n[:B]
+        lg = float(trg.train_batch(u, p, n))
+        le = float(tre.train_batch(u, p, n))
+        assert abs(lg - le) <= 2e-5 * max(1.0, abs(le)), (i, B, lg, le)
+        junk.append(torch.full((1 << (16 + i % 4),), float(i), device="cuda"))      # churn the caching allocator between replays
+        if i % 3 == 2:
+            junk.clear()
+    assert trg.hot._graph is not None                                               # a single graph, whatever the batch length
+    sg, se = trg.model_mm.state_dict(), tre.model_mm.state_dict()
+    for k in sg:
+        if not k.startswith("batch_norm"):
+            torch.testing.assert_close(sg[k], se[k], rtol=2e-5, atol=2e-7)
+    for t in junk:
+        assert float(t[0]) == float(t[-1])                                          # nothing scribbled over live memory

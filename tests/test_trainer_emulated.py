@@ -16,7 +16,7 @@ REPO = os.path.dirname(HERE)
 
 class _Slot:
     def __init__(self, cap):
-        self.host = torch.empty((3, cap), dtype=torch.int32)
+        self.host = torch.zeros((4, cap), dtype=torch.int32)
         self.np = self.host.numpy()
         self.event = SimpleNamespace(synchronize=lambda: None, record=lambda: None)
 

@@ -17,12 +17,28 @@ class _Slot:
     syncs = 0
 
     def __init__(self, cap):
-        self.host = torch.empty((3, cap), dtype=torch.int32)
+        self.host = torch.zeros((4, cap), dtype=torch.int32)
         self.np = self.host.numpy()
         self.event = SimpleNamespace(synchronize=self._sync, record=lambda: None)
 
     def _sync(self):
         _Slot.syncs += 1
+
+
+class _Hot:
+    """Stand-in for engine.HotPath's static index buffer (what Trainer stages batches into)."""
+
+    def __init__(self, batch):
+        self.batch, self.buf = batch, None
+
+    def index_buffer(self, need):
+        need = max(int(need), 2 * self.batch)
+        if self.buf is None or self.buf.shape[1] < need:
+            self.buf = torch.zeros((4, need), dtype=torch.int32)
+        return self.buf
+
+    def meta_row(self, B):
+        return int(B), int((1 - 0.71) * B)
 
 
 def _trainer(tiny_root, sampler, monkeypatch, batch=128):
@@ -34,6 +50,7 @@ def _trainer(tiny_root, sampler, monkeypatch, batch=128):
     tr.n_users, tr.n_items = gen.n_users, gen.n_items
     tr.augmented_sample_dict = pickle.load(open(os.path.join(ddir, "augmented_sample_dict"), "rb"))
     tr._slots, tr._slot_i, tr._idx_dev, tr._batch_sampler = [], 0, None, None
+    tr.hot = _Hot(batch)
     if sampler == "native":
         rp, col = gen.csr("train")
         tr._batch_sampler = BatchSampler(gen.exist_users, rp, col, gen.n_items, batch,

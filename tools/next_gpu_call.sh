@@ -34,3 +34,5 @@ for name in ("rows", "panels"):
     except Exception as e:
         print(name, "no line:", e)
 PY
+echo "== SpMM at the 10M x 1M x 200M synthetic scale: gather variants and column windows (1 GPU)"
+for v in 0 1 3; do LLMREC_SPMM_VARIANT=$v COLWIN=$([ $v = 0 ] && echo 2,4,8) timeout 400 python tools/spmm_scale.py 1.0 2>&1 | tail -12; done | tee $O/spmm_scale.txt
