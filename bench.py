@@ -244,7 +244,7 @@ def run_workload(name, a, K, W, min_seconds, with_families=True, hoist=False):
     out = {"workload": workload_string(name), "ms_per_step": round(t["ms"] / K, 4), "value": round(t["value"], 1), "unit": "interactions/s",
            "blocks": t["blocks"], "ms_per_step_min": round(t["ms_min"] / K, 4), "ms_per_step_max": round(t["ms_max"] / K, 4),
            "e2e": e2e, "gpu_launches": t["launches"], "train_edges": int(gen.n_train)}
-    if with_families:
+    if with_families and not hoist:
         fam = family_times(tr, t["dev_batches"][0])
         bytes_ = step_bytes(tr.hot, tr.graph.nnz)
         hbm, tf, src = peaks()

@@ -67,6 +67,8 @@ typedef struct {
   const int32_t* split_first; /* [n_split+1] first piece (tile id) of each split row */
   float* scratch;             /* [n_split_tiles * min(nseg,16) * d] partial sums of the pieces */
   int32_t n_tiles, n_split, n_split_tiles, _pad;
+  const uint32_t* src_mask;   /* optional bitmask over SOURCE rows (= pattern columns): a clear bit promises that row of X is all zero;
+                                 its fetch is skipped (identical sums).  NULL = every row is live. */
 } llmrec_spmm_tiling;
 
 /* Host-side planner (runs once per graph): tiles of <= tile_nnz (8..248) non-zeros, each a run of <= max_rows (<= 15)
@@ -82,6 +84,25 @@ int llmrec_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, const float* 
                         int32_t n_rows, int32_t n_cols, int32_t d,
                         const llmrec_spmm_seg* segs_host, int32_t nseg,
                         const llmrec_spmm_tiling* tiling_host, llmrec_stream_t stream);
+
+/* Row-LIST form of the same product: only rows[0 .. *n_rows_dev) (device list, device-side length, capped at max_rows; entries < 0 skipped)
+ * are computed and written; all other rows of Y are left untouched.  One segment, d in {32, 64, 128}.  For the products of a training
+ * step that are provably consumed on a small row subset (the last propagation layer reaches the loss only through the batch's
+ * neighbourhood -- dist.py "demand" mode).  Persistent grid, no host synchronisation. */
+int llmrec_spmm_rows_f32(const int32_t* rowptr, const int32_t* col, const float* vals, const float* row_scale, const float* col_scale,
+                         int32_t d, const llmrec_spmm_seg* seg_host, const int32_t* rows, const int32_t* n_rows_dev, int32_t max_rows,
+                         const uint32_t* src_mask, llmrec_stream_t stream);
+int llmrec_row_softmax_bwd_rows_f32(const float* S, int64_t lds, const float* dS, int64_t ldds, float* dX, int64_t lddx,
+                                    const int32_t* rows, const int32_t* n_rows_dev, int32_t max_rows, int32_t d, llmrec_stream_t stream);
+/* Device-side row sets: mask |= {col[e] : e in rows list[.] of the CSR}, mask |= {ids}, and mask -> (unordered) id list with *count += #bits. */
+int llmrec_mark_neighbors(const int32_t* rowptr, const int32_t* col, const int32_t* list, int32_t n_list, uint32_t* mask, llmrec_stream_t stream);
+int llmrec_mark_ids(const int32_t* ids, int32_t n, uint32_t* mask, llmrec_stream_t stream);
+int llmrec_compact_mask(const uint32_t* mask, int32_t n_bits, int32_t* list_out, int32_t* count, llmrec_stream_t stream);
+int llmrec_zero_rows_f32(float* Y, int64_t ldy, const int32_t* idx, int32_t n, int32_t d, llmrec_stream_t stream);
+int llmrec_assign_rows_f32(const float* G, int64_t ldg, const int32_t* idx, int32_t n, int32_t d, float* Y, int64_t ldy, llmrec_stream_t stream);
+/* Dense AdamW over one [n_rows x width] table whose gradient is row-sparse: g is read only where row_mask has the row's bit set. */
+int llmrec_adamw_step_rows_f32(float* p, const float* g, float* m, float* v, int64_t n_rows, int32_t width, const uint32_t* row_mask,
+                               const double* state, float lr, float beta1, float beta2, float eps, float weight_decay, llmrec_stream_t stream);
 
 /* Row softmax Y = softmax(X, dim=-1) and its backward dX = S*(dS - sum(dS*S)) (Models.py:174-175). */
 int llmrec_row_softmax_f32(const float* X, int64_t ldx, float* Y, int64_t ldy, int64_t n, int32_t d, llmrec_stream_t stream);
@@ -143,7 +164,9 @@ int64_t llmrec_proj_wgrad_group_scratch(const llmrec_proj_wgrad_problem* probs_h
  * d x_t (+)= coef[t] * (g - y_t (y_t . g)) / max(||x_t||,1e-12),  y_t = x_t/max(||x_t||,1e-12).
  * Pointer tables are HOST arrays (copied into the launch parameters).
  * --------------------------------------------------------------------------------------------- */
-/* rows: optional int32 device list of row ids to process (NULL = rows 0..n-1; n = list length otherwise). */
+/* rows: optional int32 device list of row ids to process (NULL = rows 0..n-1; n = list length otherwise).
+ * llmrec_fuse_fwd_f32 with rows != NULL and n < 0: COMPACT form over |n| list entries -- the layer tables are read at rows[b], the
+ * side operands and `out` at the compact position b (side features projected on the batch's rows only, hoisted mode). */
 int llmrec_fuse_fwd_f32(const float* const* layers_host, const int64_t* ld_layers_host, int32_t n_layers,
                         const float* const* sides_host, const int64_t* ld_sides_host, const float* coef_host,
                         int32_t n_sides, float* out, int64_t ldo, const int32_t* rows, int64_t n, int32_t d,
@@ -237,6 +260,13 @@ int llmrec_topk_hits(const int32_t* idx, int32_t n_batch, int32_t K, const int32
                      const int32_t* truth_rowptr, const int32_t* truth_col, uint8_t* hits,
                      llmrec_stream_t stream);
 
+/* test_flag == 'full' (utility/batch_test.py:38-68, utility/metrics.py:95-100): per-user ROC-AUC of the exact fp32 scores over the
+ * candidates (all items minus the user's mask row), positives = the user's truth row; 0 when either class is empty (the
+ * reference swallows sklearn's ValueError).  mask / truth rows sorted ascending.  out_auc fp32[n_batch]. */
+int llmrec_user_auc_f32(const float* U, int64_t ldu, const float* I, int64_t ldi, const int32_t* users, int32_t n_batch, int32_t n_items, int32_t d,
+                        const int32_t* mask_rowptr, const int32_t* mask_col, const int32_t* truth_rowptr, const int32_t* truth_col,
+                        float* out_auc, llmrec_stream_t stream);
+
 /* Host-side (CPU, no GPU needed) BPR item sampler, bit-identical to Data.sample()'s numpy draws
  * (utility/load_data.py:166-187): hand over numpy's legacy MT19937 state (np.random.get_state()), get the
  * positives / rejection-sampled negatives for `users` and the advanced state back.  All pointers HOST. */
@@ -270,6 +300,25 @@ int llmrec_gather_rows_f32(const float* X, int64_t ldx, const int32_t* idx, int3
                            llmrec_stream_t stream);
 int llmrec_scatter_add_rows_f32(const float* G, int64_t ldg, const int32_t* idx, int32_t n, int32_t d, float* Y, int64_t ldy,
                                 llmrec_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Hoisted side-feature mode (Models.py:145-167 with dropout p = 0 and the mask branch off):
+ * iu.ui.(X W^T + 1 b^T) = (iu.ui.X) W^T + (iu.ui.1) b^T, so the propagated TABLES are precomputed once and a step projects
+ * only the gathered rows of its batch.  The three helpers below are what that needs besides gather / projection / wgrad:
+ *   rank1_add      Y[r, c] += scale[r * lds] * bias[c]          (the (iu.ui.1) b^T term on the compact rows)
+ *   scaled_colsum  out[c] (+)= sum_terms sum_r scale[r * lds] * G[r * ldg + c]   (bias gradient; scale == NULL means 1)
+ *   feat_reg_gram  feat_reg (main.py:151-156) over ALL rows through the k x k Gram matrix of a propagated table X~ and
+ *                  h = X~^T s, n2 = |s|^2:  loss += c/2 (tr(W G W^T) + 2 b^T W h + n2 |b|^2);  dW += c (W G + b h^T);
+ *                  db += c (W h + n2 b).  scratch: d + 4 floats zeroed once (ticket re-zeroed by the kernel).
+ * --------------------------------------------------------------------------------------------- */
+typedef struct { float* Y; const float* scale; const float* bias; int64_t ldy, lds, n; int32_t width, _pad; } llmrec_rank1_block;
+typedef struct { const float* G; const float* scale; int64_t ldg, lds, n; } llmrec_colsum_term;
+int llmrec_rank1_add_f32(const llmrec_rank1_block* blocks_host, int32_t n_blocks, llmrec_stream_t stream);
+int llmrec_scaled_colsum_f32(const llmrec_colsum_term* terms_host, int32_t n_terms, int32_t width, float* out, int32_t accumulate,
+                             float* scratch /* llmrec_scaled_colsum_scratch(width) floats, zeroed once */, llmrec_stream_t stream);
+int64_t llmrec_scaled_colsum_scratch(int32_t width);
+int llmrec_feat_reg_gram_f32(const float* W, const float* bias, const float* G, const float* h, float n2, int32_t d, int32_t k, float c,
+                             float* dW, float* db, float* loss_accum, float* scratch, llmrec_stream_t stream);
 
 /* small utilities used by the host mirror */
 int llmrec_fill_f32(float* p, int64_t n, float v, llmrec_stream_t stream);

@@ -6,8 +6,9 @@ initial weights, Models.py:30-42), state-dict names image_trans/text_trans/user_
 user_id_embedding/item_id_embedding (+ the unused batch_norm), and the 14-tuple returned by
 forward (Models.py:199).  The four image_/text_ graph arguments are accepted and ignored, as in the
 reference.  Autograd works through one torch.autograd.Function whose backward is the hand-written
-backward schedule of engine.HotPath.  Out of scope: --mask / mask_rate > 0
-and drop_rate > 0 raise NotImplementedError instead of silently differing.
+backward schedule of engine.HotPath.  The optional feature-mask / dropout / attribute-restoration branch (Models.py:131-142,203-225; main.py:258-271; off by default) is
+the eager path of main.Trainer (`Trainer._train_batch_masked`); the autograd entry point MM_Model.forward itself
+raises for those flags instead of silently differing.
 """
 import torch
 import torch.nn as nn
@@ -97,13 +98,12 @@ class MM_Model(nn.Module):
     def item_feats(self):
         return {k: getattr(self, "item_feat__" + k) for k in self._item_keys}
 
-    def hot_path(self, ui_graph, iu_graph) -> HotPath:
-        """The fused executor bound to this model's parameters and a (ui, iu) graph pair."""
-        key = (id(ui_graph), id(iu_graph), self.user_id_embedding.weight.data_ptr())
+    def hot_path(self, ui_graph, iu_graph, hoisted=False, graph_scalars=None) -> HotPath:
+        """The fused executor bound to this model's parameters and a (ui, iu) graph pair.  hoisted=True builds the engine of
+        hoist.py (constant side-feature propagation precomputed; needs `graph_scalars` = BipartiteGraph.ones_propagated())."""
+        key = (id(ui_graph), id(iu_graph), self.user_id_embedding.weight.data_ptr(), bool(hoisted))
         if self._hp is None or self._hp_key != key:
             args = get_args()
-            if getattr(args, "hoist_side", 0):
-                raise NotImplementedError("--hoist_side 1 is not wired in this build")
             if not _on_device(self.user_id_embedding.weight):
                 raise RuntimeError("MM_Model runs on the B200 kernels only: move it to CUDA first (no CPU path)")
             ui_f, ui_b = operators_from_coo(ui_graph)
@@ -114,16 +114,22 @@ class MM_Model(nn.Module):
                                 user_cat_rate=args.user_cat_rate, item_cat_rate=args.item_cat_rate, aug_mf_rate=args.aug_mf_rate,
                                 mm_mf_rate=args.mm_mf_rate, prune_loss_drop_rate=args.prune_loss_drop_rate,
                                 feat_reg_decay=args.feat_reg_decay, regs0=eval(args.regs)[0], batch_size=args.batch_size,
+                                aug_sample_rate=args.aug_sample_rate,
                                 proj_mode=PROJ_MODE[getattr(args, "proj_mode", "3xtf32")],
                                 feat_layout=1 if getattr(args, "feat_layout", "rows") == "panels" else 0)
-            self._hp = HotPath((ui_f, iu_f, ui_b, iu_b), params, feats, cfg)
+            if hoisted:
+                from .hoist import HoistedHotPath
+                self._hp = HoistedHotPath((ui_f, iu_f, ui_b, iu_b), params, feats, cfg, graph_scalars)
+            else:
+                self._hp = HotPath((ui_f, iu_f, ui_b, iu_b), params, feats, cfg)
             self._hp_key = key
         return self._hp
 
     def forward(self, ui_graph, iu_graph, image_ui_graph=None, image_iu_graph=None, text_ui_graph=None, text_iu_graph=None):
         args = get_args()
         if args.mask or args.mask_rate > 0 or args.drop_rate > 0:
-            raise NotImplementedError("mask / dropout branch of MM_Model (Models.py:131-142) is out of scope of the B200 hot path")
+            raise NotImplementedError("MM_Model.forward under autograd covers the default flags; the mask / dropout branch (Models.py:131-142) "
+                                      "runs through main.Trainer (Trainer._train_batch_masked)")
         if args.layers < 1:
             raise NameError("args.layers must be >= 1 (the reference leaves image_user_feats undefined otherwise, Models.py:152)")
         hp = self.hot_path(ui_graph, iu_graph)
@@ -135,3 +141,20 @@ class MM_Model(nn.Module):
         att_i = {k: out[9 + K + j] for j, k in enumerate(hp.keys)}
         u_mask_nodes = torch.empty(0, dtype=torch.int64)          # int(mask_rate * n_users) == 0 (Models.py:139-141)
         return U, I, img_i, txt_i, img_u, txt_u, p_usr, att_i, prof_u, prof_i, att_u, att_i, None, u_mask_nodes
+
+
+class Decoder(nn.Module):
+    """Attribute-restoration head of the mask branch (Models.py:203-225): one Linear(embed_size -> feat_size) + LeakyReLU per side.
+    The reference writes nn.LeakyReLU(True), i.e. negative_slope = 1.0 -- an identity; kept.  Constructed right after MM_Model so that
+    the CPU generator is consumed in the reference's order (main.py:95-97); its optimizer is never stepped upstream (main.py:106-110)."""
+
+    def __init__(self, feat_size):
+        super().__init__()
+        d = get_args().embed_size
+        self.feat_size = feat_size
+        self.u_net = nn.Sequential(nn.Linear(d, int(feat_size)), nn.LeakyReLU(True))
+        self.i_net = nn.Sequential(nn.Linear(d, int(feat_size)), nn.LeakyReLU(True))
+
+    def forward(self, u, i):
+        """u: [n_u x d]; i: {key: [n_i x d]} -> ([n_u x feat], [n_keys x n_i x feat])"""
+        return self.u_net(u.float()), self.i_net(torch.stack([i[k] for k in i.keys()]).float())

@@ -25,7 +25,7 @@ class SpmmSeg(C.Structure):
 
 class SpmmTiling(C.Structure):
     _fields_ = [("tiles", C.c_void_p), ("split_row", C.c_void_p), ("split_first", C.c_void_p), ("scratch", C.c_void_p),
-                ("n_tiles", C.c_int32), ("n_split", C.c_int32), ("n_split_tiles", C.c_int32), ("_pad", C.c_int32)]
+                ("n_tiles", C.c_int32), ("n_split", C.c_int32), ("n_split_tiles", C.c_int32), ("_pad", C.c_int32), ("src_mask", C.c_void_p)]
 
 
 class ProjFwdProblem(C.Structure):
@@ -49,6 +49,15 @@ class GradRegion(C.Structure):
                 ("width", C.c_int32), ("c", C.c_float)]
 
 
+class Rank1Block(C.Structure):
+    _fields_ = [("Y", C.c_void_p), ("scale", C.c_void_p), ("bias", C.c_void_p), ("ldy", C.c_int64), ("lds", C.c_int64), ("n", C.c_int64),
+                ("width", C.c_int32), ("_pad", C.c_int32)]
+
+
+class ColsumTerm(C.Structure):
+    _fields_ = [("G", C.c_void_p), ("scale", C.c_void_p), ("ldg", C.c_int64), ("lds", C.c_int64), ("n", C.c_int64)]
+
+
 # name -> (restype, argtypes); must list every symbol of include/llmrec_b200.h (checked by tests)
 SIGNATURES = {
     "llmrec_abi_version": (C.c_int, []),
@@ -57,6 +66,14 @@ SIGNATURES = {
     "llmrec_spmm_csr_f32": (C.c_int, [c_i32p, c_i32p, c_f32p, c_f32p, c_f32p, C.c_int32, C.c_int32, C.c_int32,
                                       C.POINTER(SpmmSeg), C.c_int32, C.POINTER(SpmmTiling), c_stream]),
     "llmrec_spmm_plan_tiles": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "llmrec_spmm_rows_f32": (C.c_int, [c_i32p, c_i32p, c_f32p, c_f32p, c_f32p, C.c_int32, C.POINTER(SpmmSeg), c_i32p, c_i32p, C.c_int32, C.c_void_p, c_stream]),
+    "llmrec_row_softmax_bwd_rows_f32": (C.c_int, [c_f32p, C.c_int64, c_f32p, C.c_int64, c_f32p, C.c_int64, c_i32p, c_i32p, C.c_int32, C.c_int32, c_stream]),
+    "llmrec_mark_neighbors": (C.c_int, [c_i32p, c_i32p, c_i32p, C.c_int32, C.c_void_p, c_stream]),
+    "llmrec_mark_ids": (C.c_int, [c_i32p, C.c_int32, C.c_void_p, c_stream]),
+    "llmrec_compact_mask": (C.c_int, [C.c_void_p, C.c_int32, c_i32p, c_i32p, c_stream]),
+    "llmrec_zero_rows_f32": (C.c_int, [c_f32p, C.c_int64, c_i32p, C.c_int32, C.c_int32, c_stream]),
+    "llmrec_assign_rows_f32": (C.c_int, [c_f32p, C.c_int64, c_i32p, C.c_int32, C.c_int32, c_f32p, C.c_int64, c_stream]),
+    "llmrec_adamw_step_rows_f32": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, c_stream]),
     "llmrec_row_softmax_f32": (C.c_int, [c_f32p, C.c_int64, c_f32p, C.c_int64, C.c_int64, C.c_int32, c_stream]),
     "llmrec_row_softmax_bwd_f32": (C.c_int, [c_f32p, C.c_int64, c_f32p, C.c_int64, c_f32p, C.c_int64, C.c_int64, C.c_int32, c_stream]),
     "llmrec_proj_fwd_f32": (C.c_int, [c_f32p, C.c_int64, c_f32p, c_f32p, c_f32p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, c_f32p, c_stream]),
@@ -86,6 +103,7 @@ SIGNATURES = {
                                         C.c_int32, c_i32p, c_f32p, C.c_int32, c_f32p, C.c_int64, c_stream]),
     "llmrec_score_topk_scratch": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "llmrec_topk_hits": (C.c_int, [c_i32p, C.c_int32, C.c_int32, c_i32p, c_i32p, c_i32p, C.c_void_p, c_stream]),
+    "llmrec_user_auc_f32": (C.c_int, [c_f32p, C.c_int64, c_f32p, C.c_int64, c_i32p, C.c_int32, C.c_int32, C.c_int32, c_i32p, c_i32p, c_i32p, c_i32p, c_f32p, c_stream]),
     "llmrec_host_sample_items": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "llmrec_host_sample_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                            C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
@@ -93,6 +111,10 @@ SIGNATURES = {
     "llmrec_row_scale_softmax_f32": (C.c_int, [c_f32p, C.c_int64, c_f32p, c_f32p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, c_stream]),
     "llmrec_gather_rows_f32": (C.c_int, [c_f32p, C.c_int64, c_i32p, C.c_int32, C.c_int32, c_f32p, C.c_int64, c_stream]),
     "llmrec_scatter_add_rows_f32": (C.c_int, [c_f32p, C.c_int64, c_i32p, C.c_int32, C.c_int32, c_f32p, C.c_int64, c_stream]),
+    "llmrec_rank1_add_f32": (C.c_int, [C.POINTER(Rank1Block), C.c_int32, c_stream]),
+    "llmrec_scaled_colsum_f32": (C.c_int, [C.POINTER(ColsumTerm), C.c_int32, C.c_int32, c_f32p, C.c_int32, c_f32p, c_stream]),
+    "llmrec_scaled_colsum_scratch": (C.c_int64, [C.c_int32]),
+    "llmrec_feat_reg_gram_f32": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_float, C.c_int32, C.c_int32, C.c_float, c_f32p, c_f32p, c_f32p, c_f32p, c_stream]),
     "llmrec_fill_f32": (C.c_int, [c_f32p, C.c_int64, C.c_float, c_stream]),
     "llmrec_panelize_f32": (C.c_int, [c_f32p, C.c_int64, C.c_int64, C.c_int32, c_f32p, c_stream]),
 }

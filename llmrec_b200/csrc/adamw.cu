@@ -46,9 +46,42 @@ __global__ void __launch_bounds__(256) adamw_kernel(const AdamParams a) {
   for (int64_t i = n4 * 4 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride)
     adam1(p[i], g[i], m[i], v[i], decay, a.b1, a.b2, a.eps, step, bc2s);
 }
+// One [n_rows x w] table whose gradient is ROW-SPARSE: g is read only for rows whose bit is set in `row_mask`, every other row takes the
+// g = 0 update (weight decay and moment decay still apply: the reference's AdamW is dense, main.py:100-104).  24 B/param instead of 28,
+// and no dense gradient buffer has to be zeroed and written per step (the user table of the large synthetic graph: 5 GB each).
+__global__ void __launch_bounds__(256) adamw_rows_kernel(float* p, const float* g, float* m, float* v, int64_t n_rows, int w4, const unsigned* row_mask,
+                                                         const double* state, float lr, float b1, float b2, float eps, float wd) {
+  const float step = (float)state[1], bc2s = (float)state[2];
+  const float decay = 1.f - lr * wd;
+  const int64_t total = n_rows * (int64_t)w4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / w4;
+    const bool on = (__ldg(row_mask + (r >> 5)) >> (r & 31)) & 1u;
+    float4 pp = reinterpret_cast<float4*>(p)[i], mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+    const float4 gg = on ? reinterpret_cast<const float4*>(g)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    adam1(pp.x, gg.x, mm.x, vv.x, decay, b1, b2, eps, step, bc2s);
+    adam1(pp.y, gg.y, mm.y, vv.y, decay, b1, b2, eps, step, bc2s);
+    adam1(pp.z, gg.z, mm.z, vv.z, decay, b1, b2, eps, step, bc2s);
+    adam1(pp.w, gg.w, mm.w, vv.w, decay, b1, b2, eps, step, bc2s);
+    reinterpret_cast<float4*>(p)[i] = pp; reinterpret_cast<float4*>(m)[i] = mm; reinterpret_cast<float4*>(v)[i] = vv;
+  }
+}
 }  // namespace llmrec
 
 using namespace llmrec;
+
+extern "C" int llmrec_adamw_step_rows_f32(float* p, const float* g, float* m, float* v, int64_t n_rows, int32_t width, const uint32_t* row_mask,
+                                          const double* state, float lr, float beta1, float beta2, float eps, float weight_decay, llmrec_stream_t stream) {
+  LLMREC_REQUIRE_DEVICE();
+  LLMREC_CHECK_ARG(width >= 4 && width % 4 == 0 && row_mask && aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v), "adamw_rows: width %% 4 == 0, a row mask and 16-byte aligned tensors required");
+  if (n_rows <= 0) return 0;
+  int64_t bx = (n_rows * (width / 4) + 255) / 256;
+  if (bx > 148 * 8) bx = 148 * 8;
+  adamw_rows_kernel<<<(unsigned)bx, 256, 0, as_stream(stream)>>>(p, g, m, v, n_rows, width / 4, row_mask, state, lr, beta1, beta2, eps, weight_decay);
+  LLMREC_CHECK_LAUNCH("adamw_rows");
+  return 0;
+}
+
 
 extern "C" int llmrec_adamw_advance(double* state, double lr, double beta1, double beta2, llmrec_stream_t stream) {
   LLMREC_REQUIRE_DEVICE();

@@ -17,6 +17,7 @@ struct FuseParams {
   float* out; int64_t ldo;           // fwd: out; bwd: d_layer (may be null)
   const float* g; int64_t ldg;       // bwd only
   const int* rows; int64_t n; int d; int accumulate;
+  int compact;                       // fwd only: layers are read at rows[item], sides and out at the compact position `item`
 };
 
 template <int LPR>
@@ -32,11 +33,14 @@ __global__ void __launch_bounds__(256) fuse_fwd_kernel(const FuseParams p) {
   __shared__ float sc[8][RPW][kMaxSides];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane / LPR, li = lane % LPR;
   const int64_t item = ((int64_t)blockIdx.x * 8 + wib) * RPW + sub;
-  const bool valid = item < p.n;
-  const int64_t row = valid ? (p.rows ? (int64_t)p.rows[item] : item) : 0;
+  const bool in_range = item < p.n;
+  const int64_t lrow = in_range ? (p.rows ? (int64_t)p.rows[item] : item) : 0;
+  const bool valid = in_range && lrow >= 0;          // a negative list entry = "not mine": compact output row of zeros, nothing read
+  const int64_t row = valid ? lrow : 0;
+  const int64_t srow = (p.compact && in_range) ? item : row;
   const int nq = VEC ? p.d / 4 : p.d;
   for (int t = 0; t < p.n_sides; ++t) {
-    const float* x = p.sides[t] + row * p.ld_sides[t];
+    const float* x = p.sides[t] + srow * p.ld_sides[t];
     float ss = 0.f;
     if (valid) {
       for (int q = li; q < nq; q += LPR) {
@@ -48,9 +52,15 @@ __global__ void __launch_bounds__(256) fuse_fwd_kernel(const FuseParams p) {
     if (li == 0) sc[wib][sub][t] = p.coef[t] / fmaxf(sqrtf(ss), kNormEps);
   }
   __syncwarp();
-  if (!valid) return;
+  if (!valid) {
+    if (p.compact && in_range) {
+      float* z = p.out + srow * p.ldo;
+      for (int q = li; q < nq; q += LPR) { if (VEC) st4(z + q * 4, make_float4(0.f, 0.f, 0.f, 0.f)); else z[q] = 0.f; }
+    }
+    return;
+  }
   const float inv_l = 1.0f / (float)p.n_layers;
-  float* o = p.out + row * p.ldo;
+  float* o = p.out + srow * p.ldo;
   for (int q = li; q < nq; q += LPR) {
     if (VEC) {
       float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -59,13 +69,13 @@ __global__ void __launch_bounds__(256) fuse_fwd_kernel(const FuseParams p) {
         a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
       }
       a.x *= inv_l; a.y *= inv_l; a.z *= inv_l; a.w *= inv_l;
-      for (int t = 0; t < p.n_sides; ++t) fma4(a, sc[wib][sub][t], ldg4(p.sides[t] + row * p.ld_sides[t] + q * 4));
+      for (int t = 0; t < p.n_sides; ++t) fma4(a, sc[wib][sub][t], ldg4(p.sides[t] + srow * p.ld_sides[t] + q * 4));
       st4(o + q * 4, a);
     } else {
       float a = 0.f;
       for (int l = 0; l < p.n_layers; ++l) a += p.layers[l][row * p.ld_layers[l] + q];
       a *= inv_l;
-      for (int t = 0; t < p.n_sides; ++t) a = fmaf(sc[wib][sub][t], p.sides[t][row * p.ld_sides[t] + q], a);
+      for (int t = 0; t < p.n_sides; ++t) a = fmaf(sc[wib][sub][t], p.sides[t][srow * p.ld_sides[t] + q], a);
       o[q] = a;
     }
   }
@@ -163,7 +173,8 @@ extern "C" int llmrec_fuse_fwd_f32(const float* const* layers, const int64_t* ld
   p.n_layers = n_layers; p.n_sides = n_sides;
   for (int l = 0; l < n_layers; ++l) { p.layers[l] = layers[l]; p.ld_layers[l] = ld_layers[l]; vec = vec && aligned16(layers[l]) && ld_layers[l] % 4 == 0; }
   for (int t = 0; t < n_sides; ++t) { p.sides[t] = sides[t]; p.ld_sides[t] = ld_sides[t]; p.coef[t] = coef[t]; vec = vec && aligned16(sides[t]) && ld_sides[t] % 4 == 0; }
-  p.out = out; p.ldo = ldo; p.rows = rows; p.n = n; p.d = d;
+  p.out = out; p.ldo = ldo; p.rows = rows; p.n = n < 0 ? -n : n; p.d = d;
+  p.compact = (n < 0 && rows) ? 1 : 0;
   return launch_fuse<false>(p, vec, as_stream(stream));
 }
 

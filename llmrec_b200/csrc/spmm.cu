@@ -28,8 +28,11 @@ struct SpmmParams {
   int n_rows; int d; int nseg; int f4_per_seg; int total_f4; int any_softmax;
   const int4* tiles; int n_tiles; int n_split_tiles; float* scratch;
   const int* split_row; const int* split_first; int n_split;
+  const unsigned* src_mask;   // optional bitmask over SOURCE rows (columns of the pattern): clear bit = row known to be zero, never fetched
+  const int* rows; const int* n_rows_dev; int max_rows;   // row-list form (spmm_rows_kernel)
   llmrec_spmm_seg seg[LLMREC_MAX_SEG];
 };
+__device__ __forceinline__ bool src_active(const unsigned* m, int c) { return (__ldg(m + (c >> 5)) >> (c & 31)) & 1u; }
 
 template <int CH>
 struct LaneChunks {
@@ -131,6 +134,7 @@ __global__ void __launch_bounds__(256, MINB) spmm_tile_kernel(const SpmmParams p
       cidx = __ldg(p.col + e);
       w = p.vals ? __ldg(p.vals + e) : 1.0f;
       if (p.cs) w *= __ldg(p.cs + cidx);
+      if (p.src_mask && !src_active(p.src_mask, cidx)) w = 0.f;   // inactive source row: contributes exactly zero, skip its fetch
     }
     const int cnt = min(LPR, len - k0);
     for (int j0 = 0; j0 < cnt; j0 += U) {
@@ -141,7 +145,7 @@ __global__ void __launch_bounds__(256, MINB) spmm_tile_kernel(const SpmmParams p
         const int jj = (j0 + u) & (LPR - 1);
         const int cj = __shfl_sync(gmask, cidx, jj, LPR);
         wj[u] = __shfl_sync(gmask, w, jj, LPR);
-        const bool live = j0 + u < cnt;
+        const bool live = j0 + u < cnt && (!p.src_mask || wj[u] != 0.f);
 #pragma unroll
         for (int c = 0; c < CH; ++c)
           x[u][c] = (live && lc.on[c]) ? ldg4(lc.xb[c] + (int64_t)cj * lc.ldx[c]) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -170,6 +174,68 @@ __global__ void __launch_bounds__(256, MINB) spmm_tile_kernel(const SpmmParams p
     }
   } else {
     for (; cur < nrows; ++cur) finish_row<CH>(p, lc, acc, row0 + cur, gmask);  // last row and trailing empty rows
+  }
+}
+
+// Row-LIST form: only the rows named in a device list are computed (and written); every other output row is left untouched.
+// Used where a training step provably needs a small subset of a product's rows (dist.py "demand" mode: the last propagation layer
+// is consumed on the batch's neighbourhood only).  Persistent grid, one lane-group per listed row, the list length is read from
+// device memory (no host sync).  One segment; d/4 lanes per row (d in {32, 64, 128}).
+template <int LPR, int U>
+__global__ void __launch_bounds__(256) spmm_rows_kernel(const SpmmParams p) {
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, lane_in = lane % LPR, sub = lane / LPR;
+  const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
+  int n = __ldg(p.n_rows_dev);
+  n = n < p.max_rows ? n : p.max_rows;
+  const llmrec_spmm_seg sg = p.seg[0];
+  const int off = lane_in * 4;
+  const long long stride = (long long)gridDim.x * (blockDim.x >> 5) * RPW;
+  for (long long idx = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + sub; idx < n; idx += stride) {
+    const int row = __ldg(p.rows + idx);
+    if (row < 0) continue;
+    const int e0 = __ldg(p.rowptr + row), e1 = __ldg(p.rowptr + row + 1);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k0 = e0; k0 < e1; k0 += LPR) {
+      const int e = k0 + lane_in;
+      int cidx = 0; float w = 0.f;
+      if (e < e1) {
+        cidx = __ldg(p.col + e);
+        w = p.vals ? __ldg(p.vals + e) : 1.0f;
+        if (p.cs) w *= __ldg(p.cs + cidx);
+        if (p.src_mask && !src_active(p.src_mask, cidx)) w = 0.f;
+      }
+      const int cnt = min(LPR, e1 - k0);
+      for (int j0 = 0; j0 < cnt; j0 += U) {
+        float4 x[U]; float wj[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int jj = (j0 + u) & (LPR - 1);
+          const int cj = __shfl_sync(gmask, cidx, jj, LPR);
+          wj[u] = __shfl_sync(gmask, w, jj, LPR);
+          const bool live = j0 + u < cnt && (!p.src_mask || wj[u] != 0.f);
+          x[u] = live ? ldg4(sg.X + (int64_t)cj * sg.ldx + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) if (j0 + u < cnt) fma4(acc, wj[u], x[u]);
+      }
+    }
+    const float sc = p.rs ? __ldg(p.rs + row) : 1.0f;
+    acc.x *= sc; acc.y *= sc; acc.z *= sc; acc.w *= sc;
+    if (sg.flags & LLMREC_SPMM_SOFTMAX) {
+      float m = fmaxf(fmaxf(acc.x, acc.y), fmaxf(acc.z, acc.w));
+      for (int o = LPR >> 1; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(gmask, m, o));
+      float4 ev = make_float4(expf(acc.x - m), expf(acc.y - m), expf(acc.z - m), expf(acc.w - m));
+      float t = (ev.x + ev.y) + (ev.z + ev.w);
+      for (int o = LPR >> 1; o > 0; o >>= 1) t += __shfl_xor_sync(gmask, t, o);
+      const float inv = 1.0f / t;
+      acc = make_float4(ev.x * inv, ev.y * inv, ev.z * inv, ev.w * inv);
+    }
+    if (sg.Z) {
+      const float4 z = *reinterpret_cast<const float4*>(sg.Z + (int64_t)row * sg.ldz + off);
+      acc.x += z.x; acc.y += z.y; acc.z += z.z; acc.w += z.w;
+    }
+    st4(sg.Y + (int64_t)row * sg.ldy + off, acc);
   }
 }
 
@@ -340,6 +406,7 @@ extern "C" int llmrec_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, co
   const bool pow2 = (f4 & (f4 - 1)) == 0;
   if (any_softmax && !(pow2 && f4 <= 32)) vec_ok = false;  // fused softmax needs a power-of-two lane group
 
+  LLMREC_CHECK_ARG(vec_ok || !(tiling && tiling->src_mask), "spmm: the source-row mask needs the vectorised kernels (d %% 4 == 0, aligned operands, a tile plan)");
   if (!vec_ok) {
     for (int s0 = 0; s0 < nseg; s0 += LLMREC_MAX_SEG) {
       SpmmParams p{};
@@ -361,6 +428,7 @@ extern "C" int llmrec_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, co
     p.tiles = reinterpret_cast<const int4*>(tiling->tiles); p.n_tiles = tiling->n_tiles;
     p.n_split_tiles = tiling->n_split_tiles; p.scratch = tiling->scratch;
     p.split_row = tiling->split_row; p.split_first = tiling->split_first; p.n_split = tiling->n_split;
+    p.src_mask = tiling->src_mask;
     LLMREC_CHECK_ARG(p.n_split == 0 || p.scratch != nullptr, "spmm: long-row pieces need the scratch buffer");
     int rc = 0;
     if (p.total_f4 <= 8) rc = launch_spmm<8, 1, 4>(p, st);
@@ -377,6 +445,28 @@ extern "C" int llmrec_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, co
     }
     if (rc) return rc;
   }
+  return 0;
+}
+
+extern "C" int llmrec_spmm_rows_f32(const int32_t* rowptr, const int32_t* col, const float* vals, const float* row_scale, const float* col_scale,
+                                    int32_t d, const llmrec_spmm_seg* seg, const int32_t* rows, const int32_t* n_rows_dev, int32_t max_rows,
+                                    const uint32_t* src_mask, llmrec_stream_t stream) {
+  LLMREC_REQUIRE_DEVICE();
+  LLMREC_CHECK_ARG(seg && rows && n_rows_dev && max_rows >= 0, "spmm_rows: row list, its device-side length and a segment are required");
+  LLMREC_CHECK_ARG((d == 32 || d == 64 || d == 128) && aligned16(seg->X) && aligned16(seg->Y) && seg->ldx % 4 == 0 && seg->ldy % 4 == 0 &&
+                   (!seg->Z || (aligned16(seg->Z) && seg->ldz % 4 == 0)), "spmm_rows: d in {32, 64, 128} and 16-byte aligned operands required (d=%d)", d);
+  if (max_rows == 0) return 0;
+  SpmmParams p{};
+  p.rowptr = rowptr; p.col = col; p.vals = vals; p.rs = row_scale; p.cs = col_scale; p.d = d; p.nseg = 1; p.seg[0] = *seg;
+  p.src_mask = src_mask; p.rows = rows; p.n_rows_dev = n_rows_dev; p.max_rows = max_rows;
+  const int lpr = d / 4, rpw = 32 / lpr;
+  long long want = ((long long)max_rows + 8LL * rpw - 1) / (8LL * rpw);
+  const int blocks = (int)(want < 148 * 8 ? want : 148 * 8);          // persistent: 8 CTAs of 8 warps per SM
+  cudaStream_t st = as_stream(stream);
+  if (lpr == 32) spmm_rows_kernel<32, 4><<<blocks, 256, 0, st>>>(p);
+  else if (lpr == 16) spmm_rows_kernel<16, 4><<<blocks, 256, 0, st>>>(p);
+  else spmm_rows_kernel<8, 4><<<blocks, 256, 0, st>>>(p);
+  LLMREC_CHECK_LAUNCH("spmm_rows");
   return 0;
 }
 
@@ -398,6 +488,23 @@ __global__ void row_softmax_kernel(const float* X, int64_t ldx, float* Y, int64_
   t = warp_sum(t);
   float inv = 1.0f / t;
   for (int j = lane; j < d; j += 32) y[j] = expf(x[j] - m) * inv;
+}
+__global__ void row_softmax_bwd_rows_kernel(const float* S, int64_t lds, const float* dS, int64_t ldds, float* dX, int64_t lddx,
+                                            const int* rows, const int* n_rows_dev, int max_rows, int d) {
+  const int lane = threadIdx.x & 31;
+  int n = __ldg(n_rows_dev);
+  n = n < max_rows ? n : max_rows;
+  for (long long idx = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); idx < n; idx += (long long)gridDim.x * (blockDim.x >> 5)) {
+    const int64_t row = rows[idx];
+    if (row < 0) continue;
+    const float* s = S + row * lds;
+    const float* g = dS + row * ldds;
+    float* o = dX + row * lddx;
+    float t = 0.f;
+    for (int j = lane; j < d; j += 32) t = fmaf(g[j], s[j], t);
+    t = warp_sum(t);
+    for (int j = lane; j < d; j += 32) o[j] = s[j] * (g[j] - t);
+  }
 }
 __global__ void row_softmax_bwd_kernel(const float* S, int64_t lds, const float* dS, int64_t ldds, float* dX, int64_t lddx, int64_t n, int d) {
   const int lane = threadIdx.x & 31;
@@ -426,5 +533,14 @@ extern "C" int llmrec_row_softmax_bwd_f32(const float* S, int64_t lds, const flo
   if (n <= 0) return 0;
   row_softmax_bwd_kernel<<<(unsigned)((n + 7) / 8), 256, 0, as_stream(stream)>>>(S, lds, dS, ldds, dX, lddx, n, d);
   LLMREC_CHECK_LAUNCH("row_softmax_bwd");
+  return 0;
+}
+extern "C" int llmrec_row_softmax_bwd_rows_f32(const float* S, int64_t lds, const float* dS, int64_t ldds, float* dX, int64_t lddx,
+                                               const int32_t* rows, const int32_t* n_rows_dev, int32_t max_rows, int32_t d, llmrec_stream_t stream) {
+  LLMREC_REQUIRE_DEVICE();
+  if (max_rows <= 0) return 0;
+  long long want = ((long long)max_rows + 7) / 8;
+  row_softmax_bwd_rows_kernel<<<(unsigned)(want < 148 * 8 ? want : 148 * 8), 256, 0, as_stream(stream)>>>(S, lds, dS, ldds, dX, lddx, rows, n_rows_dev, max_rows, d);
+  LLMREC_CHECK_LAUNCH("row_softmax_bwd_rows");
   return 0;
 }

@@ -112,8 +112,9 @@ class ShardedHotPath:
         self.nu, self.ni, self.d, self.L = nu, ni, d, L
         dev = E_i.device
         new = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
-        self.Ul = [E_u_local] + [new(nu, d) for _ in range(L)]
-        self.Il = [E_i] + [new(ni, d) for _ in range(L)]
+        zeros = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)      # layer outputs: demand mode leaves untouched rows readable
+        self.Ul = [E_u_local] + [zeros(nu, d) for _ in range(L)]
+        self.Il = [E_i] + [zeros(ni, d) for _ in range(L)]
         self.U, self.I = new(nu, d), new(ni, d)
         self.part = new(ni, d)                       # per-rank partial of an item-side product (all-reduced in place)
         self.parts = [self.part, new(ni, d)]         # backward chain ping-pong (the reduced partial IS the next gradient)
@@ -132,7 +133,13 @@ class ShardedHotPath:
         else:
             self.opt = ops.AdamW([E_u_local, E_i], lr=1e-4)
         self.comm_bytes = 0
-        self.demand = False
+        # demand-driven training step: the LAST propagation layer reaches the loss only through the batch (U_L on the batch users and
+        # on the neighbours of the batch items, I_L on the batch items), so its four products are evaluated on those rows only and the
+        # user table's gradient stays row-sparse; every value that is computed is the same sum as in the dense schedule.
+        self.demand = bool(demand) and not self.item_sharded and L >= 1 and d in (32, 64, 128)
+        if self.demand:
+            self.needU = ops.RowSet(nu, dev)        # local users whose U_L row this step reads
+            self.batchU = ops.RowSet(nu, dev)       # local batch users (rows of the user table that receive a gradient)
 
     def set_lr(self, lr):
         self.opt.lr = lr
@@ -152,19 +159,19 @@ class ShardedHotPath:
         dist.all_gather_into_tensor(full, full[self.ilo:self.ihi], group=self.group)
         self.comm_bytes += full.numel() * 2
 
-    def _exchange(self, which, src, out=None):
+    def _exchange(self, which, src, out=None, src_mask=None):
         """self.part = sum over ranks of (item-side operator `which`) . src.  With item-row pieces, the NCCL all-reduce of
         piece k runs on NCCL's stream while the SpMM of piece k+1 runs on the compute stream (NVLink transfer hidden
         behind the gather)."""
         g = self.g
         part = self.part if out is None else out
         if self.world == 1 or not g.pieces:
-            (g.iu_raw if which == "iu" else g.uiT_raw).apply([(src, part, None, False)])
+            (g.iu_raw if which == "iu" else g.uiT_raw).apply([(src, part, None, False)], src_mask=src_mask)
             self._allreduce(part)
             return
         works = []
         for lo, hi, fwd, bwd in g.pieces:
-            (fwd if which == "iu" else bwd).apply([(src, part[lo:hi], None, False)])
+            (fwd if which == "iu" else bwd).apply([(src, part[lo:hi], None, False)], src_mask=src_mask)
             works.append(dist.all_reduce(part[lo:hi], group=self.group, async_op=True))
             self.comm_bytes += (hi - lo) * self.d * 4
         for w in works:
@@ -249,7 +256,81 @@ class ShardedHotPath:
         self.g_Ei = grad_Ei
         return self.g_Eu, self.g_Ei
 
+    # -- demand-driven step (same results, rows the batch cannot reach are never computed) ---------------------------------
+    def _batch_buffers(self, B, dev):
+        if getattr(self, "_Bd", None) == B:
+            return
+        self._Bd = B
+        d = self.d
+        new = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+        self.Ub, self.gUb, self.dUb = new(B, d), new(B, d), new(B, d)
+        self.Ib, self.gIb, self.dIb = new(2 * B, d), new(2 * B, d), new(2 * B, d)
+        self.Pc, self.sic = new(2 * B, d), new(2 * B, 1)
+        self.arange = torch.arange(B, dtype=torch.int32, device=dev)
+        self.arange2 = self.arange + B
+        self.pn = torch.empty(2 * B, dtype=torch.int32, device=dev)
+        self.cnt_pn = torch.full((1,), 2 * B, dtype=torch.int32, device=dev)
+        self.work = ops.bpr_work(1, B, dev)
+
+    def _train_step_demand(self, users, pos, neg):
+        g, L, c = self.g, self.L, self.cfg
+        B = int(users.numel())
+        self._batch_buffers(B, users.device)
+        local = owner_local_index(users, self.lo, self.hi)
+        self.pn[:B].copy_(pos); self.pn[B:].copy_(neg)
+        pn = self.pn
+        # row sets of this step (device-side, no host sync)
+        self.needU.clear(); self.needU.add_neighbors(g.rowptr_i, g.col_i, pn); self.needU.add_ids(local); self.needU.compact()
+        self.batchU.clear(); self.batchU.add_ids(local)
+        rows, cnt = self.needU.list, self.needU.count
+        # ---- forward: layers 1 .. L-1 dense, layer L on the rows the loss can reach ----
+        for l in range(1, L):
+            g.ui.apply([(self.Il[l - 1], self.Ul[l], None, False)])
+            self._exchange("iu", self.Ul[l])
+            ops.row_scale_softmax(self.part, g.si, self.Il[l], False)
+        g.ui.apply_rows((self.Il[L - 1], self.Ul[L], None, True), rows, cnt)                  # U_L = softmax(ui . I_{L-1}) on needU
+        g.iu_raw.apply_rows((self.Ul[L], self.part, None, False), pn, self.cnt_pn)            # this rank's partial of R^T U_L on the batch items
+        ops.gather_rows(self.part, pn, self.Pc)
+        self._allreduce(self.Pc)                                                              # [2B' x d] instead of [ni x d]
+        ops.gather_rows(g.si.view(-1, 1), pn, self.sic)
+        ops.row_scale_softmax(self.Pc, self.sic.view(-1), self.Pc, True)                      # I_L = softmax(si (.) sum) on the batch items
+        ops.assign_rows(self.Pc, pn, self.Il[L])
+        # ---- loss head on the batch rows ----
+        ops.fuse_fwd(self.Ul, [], [], self.Ub, rows=local, compact=True)                      # owners fill, others zero
+        self._allreduce(self.Ub)
+        ops.fuse_fwd(self.Il, [], [], self.Ib, rows=pn, compact=True)
+        ops.grad_init([(self.gUb, None, 0.0), (self.gIb, None, 0.0)], self.loss)
+        n_keep = int((1 - c.prune_loss_drop_rate) * B)
+        ops.bpr_heads([(self.Ub, self.Ib, self.gUb, self.gIb, 1.0, 1.0)], self.arange, self.arange, self.arange2, n_keep,
+                      c.regs0 / c.batch_size, self.head_out, self.loss, self.work)
+        ops.fuse_bwd(self.gUb, L + 1, self.dUb, [], [], [], False)                            # the mean's share of every layer: g / (L+1)
+        ops.fuse_bwd(self.gIb, L + 1, self.dIb, [], [], [], False)
+        # ---- backward chain ----
+        ops.fill(self.dIl, 0.0)
+        ops.scatter_add_rows(self.dIb, pn, self.dIl)
+        g_cur = self.dIl
+        for l in range(L, 0, -1):
+            if l == L:
+                src = ops.row_softmax_bwd(self.Il[l], g_cur, out=self.tmpI)                   # zero outside the batch items
+                g.iuT.apply_rows((src, self.bufU, None, False), rows, cnt)                    # gU_L on needU (the only rows src reaches)
+                ops.scatter_add_rows(self.dUb, local, self.bufU)
+                ops.row_softmax_bwd_rows(self.Ul[l], self.bufU, self.bufU, rows, cnt)
+                self._exchange("uiT", self.bufU, out=self.parts[l & 1], src_mask=self.needU.mask)
+            else:
+                g.iuT.apply([(g_cur, self.bufU, None, False)])
+                ops.scatter_add_rows(self.dUb, local, self.bufU)
+                self._exchange("uiT", self.bufU, out=self.parts[l & 1])
+            g_cur = self.parts[l & 1]
+            ops.scatter_add_rows(self.dIb, pn, g_cur)                                         # + dI_{l-1} (row-sparse addend)
+        self.g_Ei = g_cur
+        ops.zero_rows(self.g_Eu, local)                                                       # grad of E_u: the batch rows only
+        ops.scatter_add_rows(self.dUb, local, self.g_Eu)
+        self.opt.step([self.g_Eu, self.g_Ei], row_masks=[self.batchU.mask, None])
+        return self.loss
+
     def train_step(self, users, pos, neg):
+        if self.demand:
+            return self._train_step_demand(users, pos, neg)
         self.forward(fuse_items=False)
         self.loss_and_output_grads(users, pos, neg)
         self.backward()

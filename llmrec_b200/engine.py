@@ -37,6 +37,7 @@ class HotPathConfig:
     feat_reg_decay: float = 1e-5
     regs0: float = 1e-5
     batch_size: int = 1024
+    aug_sample_rate: float = 0.1      # main.py:218: a batch grows by at most int(batch_size * rate) augmented triplets
     proj_mode: int = 0                # ops.PROJ_MODE
     feat_layout: int = 0              # 0 = row-major feature tables, 1 = 32-column panels (ops.PanelFeat; tcgen05 modes only)
 
@@ -151,17 +152,19 @@ class HotPath:
                 probs.sort(key=lambda t: -t[0].shape[1])                       # long-K tiles first
                 ops.proj_fwd_group(probs, d, m)
 
-    def _prop_fwd(self):
+    def _prop_fwd(self, with_feats=None):
+        """with_feats=False: the ID layers only (the hoisted mode propagates no side-feature operand)."""
         L, S = self.L, self.S
+        wf = self.has_feats if with_feats is None else with_feats
         # step t even: ui (I_{t/2} -> U_{t/2+1});  t odd: iu (U_{(t+1)/2} -> I_{(t+1)/2}); softmax on the last layer
-        n_steps = max(2 * L, 3 if self.has_feats else 0)
+        n_steps = max(2 * L, 3 if wf else 0)
         for t in range(n_steps):
             segs = []
             if t % 2 == 0:
                 l = t // 2 + 1
-                if self.has_feats and t == 0:
+                if wf and t == 0:
                     segs += [(self.blk(self.Pi, s), self.blk(self.Fu, s), None, False) for s in range(S)]                # :153,156,162
-                if self.has_feats and t == 2:
+                if wf and t == 2:
                     segs.append((self.prof_i, self.prof_u, None, False))                                               # :167
                 if l <= L:
                     segs.append((self.Il[l - 1], self.Ul[l], None, l == L))                                            # :174,178
@@ -169,7 +172,7 @@ class HotPath:
                     self.ui.apply(segs)
             else:
                 l = (t + 1) // 2
-                if self.has_feats and t == 1:
+                if wf and t == 1:
                     segs += [(self.blk(self.Fu, s), self.blk(self.Fi, s), None, False) for s in range(S)]                # :154,157,163
                     segs.append((self.P_usr, self.prof_i, None, False))                                                # :166
                 if l <= L:
@@ -209,9 +212,10 @@ class HotPath:
             ops.fuse_bwd(self.gU, L + 1, self.dUl, su, coefs, dsu, True)
             ops.fuse_bwd(self.gI, L + 1, self.dIl, si, coefs, dsi, True)
 
-    def _chain_bwd(self, gp_usr_direct=None, gpi_direct=None):
+    def _chain_bwd(self, gp_usr_direct=None, gpi_direct=None, with_feats=None):
         L, S = self.L, self.S
-        if self.has_feats:
+        wf = self.has_feats if with_feats is None else with_feats
+        if wf:
             # prof_u = ui . prof_i  ->  Gprof_i += ui^T Gprof_u
             with self._t("spmm_bwd"):
                 self.uiT.apply([(self.Gprof_u, self.Gprof_i, self.Gprof_i, False)])
@@ -225,7 +229,7 @@ class HotPath:
             else:
                 src = g_cur_I
             segs = [(src, self.bufU, self.dUl, False)]
-            if self.has_feats and l == L:
+            if wf and l == L:
                 segs += [(self.blk(self.GFi, s), self.blk(self.GFu, s), self.blk(self.GFu, s), False) for s in range(S)]
                 segs.append((self.Gprof_i, self.GP_usr, gp_usr_direct, False))
             with self._t("spmm_bwd"):
@@ -236,7 +240,7 @@ class HotPath:
                     ops.row_softmax_bwd(self.Ul[l], self.bufU, out=self.bufU)
             dst = gE_i if l == 1 else self.bufI
             segs = [(self.bufU, dst, self.dIl, False)]
-            if self.has_feats and l == L:
+            if wf and l == L:
                 segs += [(self.blk(self.GFu, s), self.blk(self.GPi, s), self.blk(gpi_direct, s) if gpi_direct is not None else None, False)
                          for s in range(S)]
             with self._t("spmm_bwd"):
@@ -255,6 +259,12 @@ class HotPath:
                 ops.proj_wgrad_group(probs, d, m)
 
     # ---- losses + their gradients w.r.t. the forward outputs ---------------------------------------------
+    def batch_capacity(self):
+        """Largest B' a step of this configuration can see: batch_size sampled + int(batch_size * aug_sample_rate) augmented
+        triplets (main.py:217-224), rounded up to a multiple of 8."""
+        c = self.cfg
+        return (c.batch_size + int(c.batch_size * c.aug_sample_rate) + 7) // 8 * 8
+
     def ensure_capacity(self, cap):
         """Index buffer [4 x cap] (rows users, pos, neg, meta = {B', n_keep}), the per-B' meta table and the BPR work block,
         sized ONCE for a batch capacity: every captured graph reads these addresses, so they are only ever replaced together
@@ -276,7 +286,7 @@ class HotPath:
         {B', n_keep}), capacity-sized buffers whose first B' entries are live (the CUDA-graph path)."""
         c = self.cfg
         B = int(users.numel())
-        self.ensure_capacity(max(B, 2 * c.batch_size))
+        self.ensure_capacity(max(B, self.batch_capacity()))
         n_keep = int((1 - c.prune_loss_drop_rate) * B)                     # main.py:161-162 (double arithmetic)
         heads = [(self.U, self.I, self.gU, self.gI, 1.0, 1.0)]                                                        # main.py:232-235
         regions = [(self.gU, None, 0.0), (self.gI, None, 0.0)]
@@ -320,7 +330,7 @@ class HotPath:
     # ---- CUDA-graph replay of the whole step -----------------------------------------------------------
     def index_buffer(self, need):
         """The static [4 x cap] int32 buffer the captured step reads: rows users / pos / neg, row 3 = {B', n_keep, ...}."""
-        self.ensure_capacity(max(int(need), 2 * self.cfg.batch_size))
+        self.ensure_capacity(max(int(need), self.batch_capacity()))
         return self._gidx
 
     def meta_row(self, B):

@@ -60,6 +60,18 @@ class BipartiteGraph:
         self.iuT = CsrOperator(self.rowptr_u, self.col_u, nu, ni, vals=self.w_iuT, plan=self.ui.plan)
         self.device = dev
 
+    def ones_propagated(self):
+        """cu = ui.1, ci = iu.ui.1, ri = iu.1, ru = ui.iu.1 -- the propagated ones-vectors that multiply the Linear biases when the
+        side-feature propagation is hoisted (hoist.py); computed with the propagation kernel itself on [n x 4] blocks."""
+        new = lambda n: torch.empty(n, 4, dtype=torch.float32, device=self.device)
+        one_i, one_u = torch.ones(self.n_items, 4, device=self.device), torch.ones(self.n_users, 4, device=self.device)
+        cu, ci, ri, ru = new(self.n_users), new(self.n_items), new(self.n_items), new(self.n_users)
+        self.ui.apply([(one_i, cu, None, False)])
+        self.iu.apply([(cu, ci, None, False)])
+        self.iu.apply([(one_u, ri, None, False)])
+        self.ui.apply([(ri, ru, None, False)])
+        return dict(cu=cu[:, 0].contiguous(), ci=ci[:, 0].contiguous(), ri=ri[:, 0].contiguous(), ru=ru[:, 0].contiguous())
+
     # the reference-facing COO tensors (what Trainer.ui_graph / iu_graph hold; main.py:128-134)
     def coo_tensors(self):
         def coo(rowptr, col, scale, shape):

@@ -27,7 +27,7 @@ import numpy as np
 import scipy.sparse as sp
 import torch
 
-from .Models import MM_Model
+from .Models import Decoder, MM_Model
 from .graph import BipartiteGraph
 from .runtime import get_args, set_args
 from .utility import batch_test
@@ -112,7 +112,16 @@ class Trainer(object):
         self.model_mm = MM_Model(self.n_users, self.n_items, self.emb_dim, self.weight_size, self.mess_dropout, self.image_feats,
                                  self.text_feats, self.user_init_embedding, self.item_attribute_embedding)   # built on CPU: RNG parity
         self.model_mm = self.model_mm.to(self.device)
-        self.hot = self.model_mm.hot_path(self.ui_graph, self.iu_graph)
+        # main.py:97: the Decoder is built right after the model (its two nn.Linear inits consume the CPU generator before the first
+        # torch.randperm of the mask branch); its optimizer exists upstream but is never stepped (main.py:106-110)
+        self.decoder = Decoder(self.user_init_embedding.shape[1]).to(self.device)
+        self.masked_mode = bool(args.mask) or args.mask_rate > 0 or args.drop_rate > 0
+        # --hoist_side 1: only sound while dropout is the identity and the mask branch is off
+        self.hoisted = bool(getattr(args, "hoist_side", 0)) and not (args.mask or args.mask_rate > 0 or args.drop_rate > 0)
+        if self.hoisted:
+            self.hot = self.model_mm.hot_path(self.ui_graph, self.iu_graph, hoisted=True, graph_scalars=self.graph.ones_propagated())
+        else:
+            self.hot = self.model_mm.hot_path(self.ui_graph, self.iu_graph)
         # torch.optim.AdamW defaults: betas (0.9, 0.999), eps 1e-8, weight_decay 0.01 (main.py:100-104)
         self.optimizer = self.hot.set_optimizer(lr=self.lr)
         self._slots, self._slot_i, self._idx_dev = [], 0, None
@@ -174,8 +183,86 @@ class Trainer(object):
         """main.py:182-187: full forward in eval mode, then test_torch."""
         self.model_mm.eval()
         with torch.no_grad():
+            if self.masked_mode:
+                self._mask_features()                 # Models.py:131-142 runs in eval mode too (and keeps mutating the feature buffers)
             ua_embeddings, ia_embeddings = self.hot.forward()
         return batch_test.test_torch(ua_embeddings, ia_embeddings, users_to_test, is_val)
+
+    # ---- optional branch: feature mask / dropout / attribute restoration (Models.py:131-150, main.py:258-271; SURVEY.md 8f-4) ---------
+    def _mask_features(self):
+        """Models.py:131-142: random rows of the attribute / profile tables are overwritten IN PLACE (persistently) with the column mean.
+        torch.randperm draws from the CPU generator in the reference's order: items first (only with --mask), then users (always)."""
+        args, m = self.args, self.model_mm
+        i_mask = None
+        if args.mask:
+            i_mask = torch.randperm(self.n_items)[:int(args.mask_rate * self.n_items)].to(self.device)
+            for k in m._item_keys:
+                f = getattr(m, "item_feat__" + k)
+                f[i_mask] = f.mean(0)
+        u_mask = torch.randperm(self.n_users)[:int(args.mask_rate * self.n_users)].to(self.device)
+        m.user_feats[u_mask] = m.user_feats.mean(0)
+        return i_mask, u_mask
+
+    @staticmethod
+    def sce_criterion(x, y, alpha=1):
+        """main.py:175-180"""
+        x = torch.nn.functional.normalize(x, p=2, dim=-1)
+        y = torch.nn.functional.normalize(y, p=2, dim=-1)
+        return (1 - (x * y).sum(dim=-1)).pow(alpha).mean()
+
+    @staticmethod
+    def mse_criterion(x, y, alpha=3):
+        """main.py:167-173 (the cosine term is computed and discarded upstream; the result is the MSE of the normalised rows)"""
+        x = torch.nn.functional.normalize(x, p=2, dim=-1)
+        y = torch.nn.functional.normalize(y, p=2, dim=-1)
+        return torch.nn.functional.mse_loss(x, y)
+
+    def _train_batch_masked(self, u, p, n):
+        """One training step with --mask / --mask_rate / --drop_rate: the same kernels, launched eagerly, with the branch-specific pieces
+        (feature masking, dropout masks, Decoder + restoration loss) as plain torch ops between them.  Off by default upstream."""
+        args, hp, m = self.args, self.hot, self.model_mm
+        i_mask, u_mask = self._mask_features()
+        hp._proj_fwd()
+        drop = None
+        if args.drop_rate > 0:
+            # nn.Dropout in training mode on each projection, reference order image, text, user, item keys (Models.py:145-150); the mask of a
+            # contiguous [n x d] tensor is drawn from the CUDA generator exactly as nn.Dropout would on the projection itself
+            d = hp.d
+            blocks = [hp.blk(hp.Pi, 0), hp.blk(hp.Pi, 1), hp.P_usr] + [hp.blk(hp.Pi, 2 + j) for j in range(len(hp.keys))]
+            drop = [torch.nn.functional.dropout(torch.ones(b.shape[0], d, device=self.device), p=args.drop_rate, training=True) for b in blocks]
+            for b, mk in zip(blocks, drop):
+                b.mul_(mk)
+        hp._prop_fwd()
+        hp._fuse_fwd()
+        hp.loss_and_output_grads(u, p, n)
+        if args.mask and args.att_re_rate != 0:
+            # main.py:258-271: decoder on the DETACHED masked profile rows (torch.tensor(...) upstream copies) and on the masked rows of the
+            # propagated attribute features (these keep their graph: the gradient flows back into GFi)
+            v = hp.side_views()
+            keys = hp.keys
+            leaf = {k: v["att_i"][k][i_mask].detach().clone().requires_grad_(True) for k in keys}
+            dec_u, dec_i = self.decoder(v["prof_u"][u_mask].detach(), leaf)
+            crit = self.mse_criterion if args.feat_loss_type == "mse" else self.sce_criterion
+            raw_u = torch.as_tensor(self.user_init_embedding[u_mask.cpu().numpy()], device=self.device).float()
+            att = crit(dec_u, raw_u, alpha=args.alpha_l)
+            for j, k in enumerate(keys):
+                raw_i = torch.as_tensor(self.item_attribute_embedding[k][i_mask.cpu().numpy()], device=self.device).float()
+                att = att + crit(dec_i[j], raw_i, alpha=args.alpha_l)
+            (args.att_re_rate * att).backward()
+            self.decoder.zero_grad(set_to_none=True)                      # de_optimizer is never stepped upstream
+            for j, k in enumerate(keys):
+                hp.blk(hp.GFi, 2 + j).index_add_(0, i_mask, leaf[k].grad)
+            hp.loss.add_(args.att_re_rate * att.detach())
+        hp._fuse_bwd()
+        hp._chain_bwd()
+        if drop is not None:                                              # backward of the dropout: the same masks on the projection gradients
+            gblocks = [hp.blk(hp.GPi, 0), hp.blk(hp.GPi, 1), hp.GP_usr] + [hp.blk(hp.GPi, 2 + j) for j in range(len(hp.keys))]
+            for b, mk in zip(gblocks, drop):
+                b.mul_(mk)
+        hp._wgrad()
+        hp.opt.step([hp.grads[k] for k in hp._opt_names])
+        self._last_dropout_masks = drop
+        return hp.loss
 
     # ---- one batch ---------------------------------------------------------------------------------------
     def sample_batch(self):
@@ -199,7 +286,7 @@ class Trainer(object):
     def _next_slot(self, need):
         """Next pinned staging slot of the ring (4 slots), free to be rewritten.  The device side of the copy is the engine's
         static index buffer (what the captured CUDA graph reads), so a batch crosses PCIe exactly once."""
-        self._idx_dev = self.hot.index_buffer(max(need, 2 * self.batch_size + 8))
+        self._idx_dev = self.hot.index_buffer(need)
         cap = self._idx_dev.shape[1]
         if not self._slots or self._slots[0].host.shape[1] != cap:
             if self._slots:
@@ -234,14 +321,17 @@ class Trainer(object):
         a pinned staging slot.  -> three device views (users, pos, neg)."""
         if self._batch_sampler is None:
             return self.upload_batch(*self.sample_batch())
-        slot = self._next_slot(2 * self._batch_sampler.batch)
+        slot = self._next_slot(self.hot.batch_capacity())
         B = self._batch_sampler.draw(slot.np[:3], self.args.aug_sample_rate)
         self.new_batch_size = B - self._batch_sampler.batch
         return self._push(slot, B)
 
     def _step(self, u, p, n):
         # u, p, n are views of the engine's index buffer (see _push): the graph replays on what was just staged
-        loss = self.hot.replay_staged() if self.use_graph else self.hot.train_step(u, p, n)
+        if self.masked_mode:
+            loss = self._train_batch_masked(u, p, n)
+        else:
+            loss = self.hot.replay_staged() if self.use_graph else self.hot.train_step(u, p, n)
         # device-side epoch accumulators: [total, mf(main), emb(main)]
         self._epoch_stats[0:1] += loss
         self._epoch_stats[1:3] += self.hot.head_out[0:2]

@@ -95,10 +95,25 @@ class CsrOperator:
             if k.scratch is not None:
                 _retired.append(k.scratch)
             k.scratch = torch.empty(need, dtype=torch.float32, device=self.rowptr.device)
-        return N.SpmmTiling(_p(k.tiles), _p(k.split_row), _p(k.split_first), _p(k.scratch), k.n_tiles, k.n_split, k.n_split_tiles, 0)
+        return N.SpmmTiling(_p(k.tiles), _p(k.split_row), _p(k.split_first), _p(k.scratch), k.n_tiles, k.n_split, k.n_split_tiles, 0, None)
 
-    def apply(self, segs):
-        """segs: list of (X, Y, Z_or_None, softmax: bool); all share d = X.shape[1]."""
+    def apply_rows(self, seg, rows, count, max_rows=None, src_mask=None):
+        """Row-list form (llmrec_spmm_rows_f32): only rows[0 .. count[0]) are computed and written.  seg = (X, Y, Z|None, softmax);
+        rows: int32 CUDA list, count: int32[1] CUDA (device-side length), src_mask: optional uint32/int32 bitmask over source rows."""
+        X, Y, Z, sm = seg
+        _mat(X, "spmm X"); _mat(Y, "spmm Y")
+        d = int(X.shape[1])
+        if X.shape[0] != self.n_cols or Y.shape[0] != self.n_rows or Y.shape[1] != d:
+            raise ValueError("spmm_rows: shape mismatch")
+        sg = N.SpmmSeg(_p(X), _p(Y), _p(Z) if Z is not None else None, _ld(X), _ld(Y), _ld(Z) if Z is not None else 0, N.SPMM_SOFTMAX if sm else 0, 0)
+        mx = int(rows.numel()) if max_rows is None else int(max_rows)
+        N.check(N.lib().llmrec_spmm_rows_f32(_p(self.rowptr), _p(self.col), _p(self.vals), _p(self.rs), _p(self.cs), d, C.byref(sg),
+                                              _p(_i32(rows)), _p(count), mx, _p(src_mask), _stream()), "spmm_rows")
+        _count()
+
+    def apply(self, segs, src_mask=None):
+        """segs: list of (X, Y, Z_or_None, softmax: bool); all share d = X.shape[1].  src_mask: optional bitmask over the SOURCE rows
+        (rows of X): a clear bit promises an all-zero row, whose fetch is skipped."""
         if not segs:
             return
         d = int(segs[0][0].shape[1])
@@ -110,6 +125,7 @@ class CsrOperator:
             arr[i] = N.SpmmSeg(_p(X), _p(Y), _p(Z) if Z is not None else None, _ld(X), _ld(Y), _ld(Z) if Z is not None else 0,
                                N.SPMM_SOFTMAX if sm else 0, 0)
         til = self._tiling_struct(d * min(len(segs), N.MAX_SEG))
+        til.src_mask = src_mask.data_ptr() if src_mask is not None else None
         N.check(N.lib().llmrec_spmm_csr_f32(_p(self.rowptr), _p(self.col), _p(self.vals), _p(self.rs), _p(self.cs),
                                              self.n_rows, self.n_cols, d, arr, len(segs), C.byref(til), _stream()), "spmm")
         _count(-(-len(segs) // N.MAX_SEG) * (2 if til.n_split > 0 else 1))
@@ -128,6 +144,52 @@ def row_softmax_bwd(S, dS, out=None):
                                                 S.shape[0], S.shape[1], _stream()), "row_softmax_bwd")
     _count()
     return out
+
+
+def row_softmax_bwd_rows(S, dS, out, rows, count, max_rows=None):
+    mx = int(rows.numel()) if max_rows is None else int(max_rows)
+    N.check(N.lib().llmrec_row_softmax_bwd_rows_f32(_p(_mat(S)), _ld(S), _p(_mat(dS)), _ld(dS), _p(_mat(out)), _ld(out), _p(_i32(rows)), _p(count), mx,
+                                                     S.shape[1], _stream()), "row_softmax_bwd_rows")
+    _count()
+    return out
+
+
+class RowSet:
+    """A set of row ids living on the device: uint32 bitmask + compacted id list + its length, rebuilt every step without a host sync."""
+
+    def __init__(self, n, device):
+        self.n = int(n)
+        self.mask = torch.zeros((self.n + 31) // 32 + 1, dtype=torch.int32, device=device)
+        self.list = torch.zeros(max(self.n, 1), dtype=torch.int32, device=device)
+        self.count = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def clear(self):
+        N.check(N.lib().llmrec_fill_f32(_p(self.mask), self.mask.numel(), 0.0, _stream()), "fill")
+        N.check(N.lib().llmrec_fill_f32(_p(self.count), 1, 0.0, _stream()), "fill")
+        _count(2)
+
+    def add_neighbors(self, rowptr, col, rows):
+        """every column id of the CSR rows named in `rows` (int32 CUDA list; entries < 0 skipped)"""
+        N.check(N.lib().llmrec_mark_neighbors(_p(_i32(rowptr)), _p(_i32(col)), _p(_i32(rows)), rows.numel(), _p(self.mask), _stream()), "mark_neighbors")
+        _count()
+
+    def add_ids(self, ids):
+        N.check(N.lib().llmrec_mark_ids(_p(_i32(ids)), ids.numel(), _p(self.mask), _stream()), "mark_ids")
+        _count()
+
+    def compact(self):
+        N.check(N.lib().llmrec_compact_mask(_p(self.mask), self.n, _p(self.list), _p(self.count), _stream()), "compact_mask")
+        _count()
+
+
+def zero_rows(Y, idx):
+    N.check(N.lib().llmrec_zero_rows_f32(_p(_mat(Y)), _ld(Y), _p(_i32(idx)), idx.numel(), Y.shape[1], _stream()), "zero_rows")
+    _count()
+
+
+def assign_rows(G, idx, Y):
+    N.check(N.lib().llmrec_assign_rows_f32(_p(_mat(G)), _ld(G), _p(_i32(idx)), idx.numel(), G.shape[1], _p(_mat(Y)), _ld(Y), _stream()), "assign_rows")
+    _count()
 
 
 PROJ_MODE = {"3xtf32": 0, "tf32": 1, "fp32": 2}
@@ -235,11 +297,16 @@ def _ld_table(tensors):
     return arr
 
 
-def fuse_fwd(layers, sides, coefs, out, rows=None):
-    """out = mean(layers) + sum_t coefs[t] * normalize(sides[t])   (Models.py:185-197)."""
+def fuse_fwd(layers, sides, coefs, out, rows=None, compact=False):
+    """out = mean(layers) + sum_t coefs[t] * normalize(sides[t])   (Models.py:185-197).
+    rows: only these rows; compact=True: layers are read at rows[b], sides and out are [len(rows) x d] blocks indexed by b."""
     for t in list(layers) + list(sides) + [out]:
         _mat(t)
     n = out.shape[0] if rows is None else rows.numel()
+    if compact:
+        if rows is None:
+            raise ValueError("fuse_fwd: compact form needs a row list")
+        n = -n
     cf = (C.c_float * max(1, len(coefs)))(*[float(c) for c in coefs])
     N.check(N.lib().llmrec_fuse_fwd_f32(_ptr_table(layers), _ld_table(layers), len(layers), _ptr_table(sides), _ld_table(sides), cf,
                                          len(sides), _p(out), _ld(out), _p(rows), n, out.shape[1], _stream()), "fuse_fwd")
@@ -323,13 +390,25 @@ class AdamW:
         self.state = torch.zeros(4, dtype=torch.float64, device=dev)
         self._n = (C.c_int64 * len(self.params))(*[p.numel() for p in self.params])
 
-    def step(self, grads):
+    def step(self, grads, row_masks=None):
+        """row_masks: optional list (one entry per parameter) of RowSet-style bitmasks or None: a masked [n x w] parameter reads its
+        gradient only on the flagged rows and takes the g = 0 update elsewhere (row-sparse gradients of a dense AdamW)."""
         lib = N.lib()
         N.check(lib.llmrec_adamw_advance(_p(self.state), self.lr, self.betas[0], self.betas[1], _stream()), "adamw_advance")
-        N.check(lib.llmrec_adamw_step_f32(_ptr_table([p.data for p in self.params]), _ptr_table(grads), _ptr_table(self.m), _ptr_table(self.v),
-                                           self._n, len(self.params), _p(self.state), self.lr, self.betas[0], self.betas[1], self.eps,
-                                           self.wd, _stream()), "adamw_step")
-        _count(1 + -(-len(self.params) // 16))
+        dense = [i for i in range(len(self.params)) if not (row_masks and row_masks[i] is not None)]
+        for i in range(len(self.params)):
+            if i in dense:
+                continue
+            p = self.params[i]
+            N.check(lib.llmrec_adamw_step_rows_f32(_p(p), _p(grads[i]), _p(self.m[i]), _p(self.v[i]), p.shape[0], p.shape[1], _p(row_masks[i]), _p(self.state),
+                                                    self.lr, self.betas[0], self.betas[1], self.eps, self.wd, _stream()), "adamw_step_rows")
+            _count()
+        if dense:
+            ps, gs, ms, vs = ([x[i] for i in dense] for x in ([p.data for p in self.params], grads, self.m, self.v))
+            n = (C.c_int64 * len(dense))(*[self.params[i].numel() for i in dense])
+            N.check(lib.llmrec_adamw_step_f32(_ptr_table(ps), _ptr_table(gs), _ptr_table(ms), _ptr_table(vs), n, len(dense), _p(self.state),
+                                               self.lr, self.betas[0], self.betas[1], self.eps, self.wd, _stream()), "adamw_step")
+        _count(1 + -(-len(dense) // 16))
 
 
 SCORE_MODE = {"3xtf32": 0, "fp32": 2}
@@ -364,6 +443,16 @@ def topk_hits(idx, users, truth_rowptr, truth_col):
     return hits
 
 
+def user_auc(U, I, users, mask_rowptr, mask_col, truth_rowptr, truth_col):
+    """fp32[n] per-user ROC-AUC over the candidates (test_flag='full', batch_test.py:38-68)."""
+    _mat(U); _mat(I)
+    out = torch.empty(users.numel(), dtype=torch.float32, device=U.device)
+    N.check(N.lib().llmrec_user_auc_f32(_p(U), _ld(U), _p(I), _ld(I), _p(_i32(users)), users.numel(), I.shape[0], I.shape[1], _p(mask_rowptr), _p(mask_col),
+                                         _p(_i32(truth_rowptr)), _p(_i32(truth_col)), _p(out), _stream()), "user_auc")
+    _count()
+    return out
+
+
 def row_scale_softmax(X, scale, out, softmax):
     N.check(N.lib().llmrec_row_scale_softmax_f32(_p(_mat(X)), _ld(X), _p(scale), _p(_mat(out)), _ld(out), X.shape[0], X.shape[1],
                                                   1 if softmax else 0, _stream()), "row_scale_softmax")
@@ -379,6 +468,55 @@ def gather_rows(X, idx, out):
 
 def scatter_add_rows(G, idx, Y):
     N.check(N.lib().llmrec_scatter_add_rows_f32(_p(_mat(G)), _ld(G), _p(_i32(idx)), idx.numel(), G.shape[1], _p(_mat(Y)), _ld(Y), _stream()), "scatter_add_rows")
+    _count()
+
+
+def _scale_col(t):
+    """1-D fp32 CUDA view (a column of a row-major table) -> (pointer, element stride)."""
+    if t is None:
+        return C.c_void_p(0), 0
+    if t.dim() != 1 or t.dtype != torch.float32 or not t.is_cuda:
+        raise ValueError("scale: need a 1-D fp32 CUDA tensor (a column view is fine)")
+    return C.c_void_p(t.data_ptr()), int(t.stride(0)) if t.numel() > 1 else 1
+
+
+def rank1_add(blocks):
+    """blocks: list of (Y[n x w], scale[n] (1-D view), bias[w]):  Y += scale (x) bias.  One launch."""
+    arr = (N.Rank1Block * len(blocks))()
+    for i, (Y, sc, b) in enumerate(blocks):
+        _mat(Y)
+        ptr, lds = _scale_col(sc)
+        arr[i] = N.Rank1Block(_p(Y), ptr, _p(b), _ld(Y), lds, Y.shape[0], Y.shape[1], 0)
+    N.check(N.lib().llmrec_rank1_add_f32(arr, len(blocks), _stream()), "rank1_add")
+    _count()
+
+
+def scaled_colsum(terms, out, accumulate=False):
+    """out[c] (+)= sum over terms (G[n x w], scale[n] | None) of sum_r scale[r] * G[r, c].  One launch, deterministic."""
+    w = int(out.numel())
+    arr = (N.ColsumTerm * len(terms))()
+    for i, (G, sc) in enumerate(terms):
+        _mat(G)
+        if G.shape[1] != w:
+            raise ValueError("scaled_colsum: width mismatch")
+        ptr, lds = _scale_col(sc)
+        arr[i] = N.ColsumTerm(_p(G), ptr, _ld(G), lds, G.shape[0])
+    key = ("colsum", out.device.index, w)
+    sc_ = _scratch.get(key)
+    if sc_ is None:
+        sc_ = _scratch[key] = torch.zeros(int(N.lib().llmrec_scaled_colsum_scratch(w)), dtype=torch.float32, device=out.device)
+    N.check(N.lib().llmrec_scaled_colsum_f32(arr, len(terms), w, _p(out), 1 if accumulate else 0, _p(sc_), _stream()), "scaled_colsum")
+    _count()
+
+
+def feat_reg_gram(W, b, G, h, n2, c, dW, db, loss):
+    """feat_reg over all rows through the Gram matrix G[k x k] of a propagated table (include/llmrec_b200.h)."""
+    d, k = W.shape
+    key = ("gram", W.device.index, d)
+    sc_ = _scratch.get(key)
+    if sc_ is None:
+        sc_ = _scratch[key] = torch.zeros(d + 4, dtype=torch.float32, device=W.device)
+    N.check(N.lib().llmrec_feat_reg_gram_f32(_p(W), _p(b), _p(G), _p(h), float(n2), d, k, float(c), _p(dW), _p(db), _p(loss), _p(sc_), _stream()), "feat_reg_gram")
     _count()
 
 

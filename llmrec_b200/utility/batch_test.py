@@ -54,8 +54,7 @@ def rank_block(ua_embeddings, ia_embeddings, user_batch, is_val, mode=None):
 def test_torch(ua_embeddings, ia_embeddings, users_to_test, is_val, drop_flag=False, batch_test_flag=False):
     nK = len(Ks)
     result = {"precision": np.zeros(nK), "recall": np.zeros(nK), "ndcg": np.zeros(nK), "hit_ratio": np.zeros(nK), "auc": 0.0}
-    if get_args().test_flag != "part":
-        raise NotImplementedError("test_flag='full' (AUC over the whole ranking, batch_test.py:38-68) is out of scope (SURVEY.md 8f-4)")
+    full = get_args().test_flag != "part"            # 'full': the same hit vectors + per-user ROC-AUC over every candidate (batch_test.py:38-68)
     test_users = np.asarray(list(users_to_test) if not isinstance(users_to_test, np.ndarray) else users_to_test, dtype=np.int32)
     n_test_users = int(test_users.shape[0])
     u_batch_size = BATCH_SIZE * 2                                             # batch_test.py:117
@@ -69,9 +68,17 @@ def test_torch(ua_embeddings, ia_embeddings, users_to_test, is_val, drop_flag=Fa
     for start in range(0, n_test_users, u_batch_size):
         user_batch = test_users[start:start + u_batch_size]
         _, hits = rank_block(ua, ia, user_batch, is_val)
-        pending.append((user_batch, hits))
-    for user_batch, hits in pending:                                          # one D2H per block, after all launches
+        auc = None
+        if full:
+            dev = ua.device
+            users_dev = torch.as_tensor(np.asarray(user_batch, dtype=np.int32)).to(dev)
+            auc = ops.user_auc(ua, ia, users_dev, *_device_csr("train", dev), *_device_csr("val" if is_val else "test", dev))
+        pending.append((user_batch, hits, auc))
+    for user_batch, hits, auc in pending:                                     # one D2H per block, after all launches
         h = hits.cpu().numpy()
+        if auc is not None:
+            for a in auc.cpu().numpy().astype(np.float64):                    # `result['auc'] += re['auc'] / n_test_users` (:165)
+                result["auc"] += a / n_test_users
         trp = data_generator.csr("val" if is_val else "test")[0]
         n_pos = (trp[user_batch + 1] - trp[user_batch]).astype(np.int64)       # len(truth[u]) per user
         rows, m = metrics.block_metrics_sparse(h, n_pos, Ks)

@@ -171,8 +171,35 @@ def init_params(cfg: OracleConfig, data: OracleData) -> dict:
 # ----------------------------------------------------------------------------------------
 # forward (Models.py:127-199, default flags: mask off, dropout p=0)
 # ----------------------------------------------------------------------------------------
-def forward(params: dict, feats: dict, ui: torch.Tensor, iu: torch.Tensor, cfg: OracleConfig) -> dict:
-    """feats: {'image','text','user': tensors, 'item': {key: tensor}} fp32."""
+def mask_features(feats: dict, n_users: int, n_items: int, mask: bool, mask_rate: float):
+    """Models.py:131-142: in-place, persistent; torch.randperm on the CPU generator, items first (only with --mask), users always."""
+    i_mask = None
+    if mask:
+        i_mask = torch.randperm(n_items)[:int(mask_rate * n_items)]
+        for k in feats["item"]:
+            feats["item"][k][i_mask] = feats["item"][k].mean(0)
+    u_mask = torch.randperm(n_users)[:int(mask_rate * n_users)]
+    feats["user"][u_mask] = feats["user"].mean(0)
+    return i_mask, u_mask
+
+
+def restoration_loss(out: dict, dec: dict, raw_user, raw_items: dict, i_mask, u_mask, alpha=2, kind="sce"):
+    """main.py:258-271 + Models.py:203-225: decoder = Linear + LeakyReLU(negative_slope=True == 1.0, an identity) per side; the profile
+    input is detached upstream (torch.tensor(...) copy), the attribute inputs keep their graph."""
+    def crit(x, y):
+        x, y = F.normalize(x, p=2, dim=-1), F.normalize(y, p=2, dim=-1)
+        return F.mse_loss(x, y) if kind == "mse" else (1 - (x * y).sum(dim=-1)).pow(alpha).mean()
+    dec_u = F.linear(out["prof_u"][u_mask].detach(), dec["u_w"], dec["u_b"])
+    loss = crit(dec_u, raw_user[u_mask])
+    for k in out["att_i"]:
+        loss = loss + crit(F.linear(out["att_i"][k][i_mask], dec["i_w"], dec["i_b"]), raw_items[k][i_mask])
+    return loss
+
+
+def forward(params: dict, feats: dict, ui: torch.Tensor, iu: torch.Tensor, cfg: OracleConfig, drop=None) -> dict:
+    """feats: {'image','text','user': tensors, 'item': {key: tensor}} fp32.
+    drop: optional list of dropout masks (already scaled by 1/(1-p)) in the reference's order image, text, user, item keys
+    (Models.py:145-150 with --drop_rate > 0); None = Dropout(p=0), the default."""
     def lin(x, name):
         return F.linear(x, params[name + ".weight"], params[name + ".bias"])
 
@@ -180,6 +207,9 @@ def forward(params: dict, feats: dict, ui: torch.Tensor, iu: torch.Tensor, cfg: 
     p_txt = lin(feats["text"], "text_trans")                              # :146
     p_usr = lin(feats["user"], "user_trans")                              # :147
     p_att = {k: lin(v, "item_trans") for k, v in feats["item"].items()}   # :148-150
+    if drop is not None:
+        p_img, p_txt, p_usr = p_img * drop[0], p_txt * drop[1], p_usr * drop[2]
+        p_att = {k: v * drop[3 + j] for j, (k, v) in enumerate(p_att.items())}
 
     spmm = torch.sparse.mm
     img_u = spmm(ui, p_img); img_i = spmm(iu, img_u)                      # :152-157 (layers>=1: same result)
@@ -334,7 +364,20 @@ def rank_users_numpy(scores, train_lists, kmax):
     return order
 
 
-def evaluate(U, I, data: OracleData, users, cfg: OracleConfig, is_val=False, faithful=True):
+def user_auc(scores_row, train_items, pos_items, n_items):
+    """test_flag='full' (batch_test.py:38-54, metrics.py:95-100): roc_auc_score of the scores of all candidates (items not in
+    train_items), label 1 for the user's truth items; 0. when sklearn refuses (a single class)."""
+    from sklearn.metrics import roc_auc_score
+    cand = sorted(set(range(n_items)) - set(train_items))
+    pos = set(pos_items)
+    y = [1 if i in pos else 0 for i in cand]
+    try:
+        return float(roc_auc_score(y_true=y, y_score=[scores_row[i] for i in cand]))
+    except Exception:
+        return 0.0
+
+
+def evaluate(U, I, data: OracleData, users, cfg: OracleConfig, is_val=False, faithful=True, full=False):
     """test_torch: blocks of 2*batch_size users, fp32 scores, per-user ranking, metrics averaged
     over n_test_users by sequential float64 accumulation (batch_test.py:112-169)."""
     Ks = list(cfg.Ks)
@@ -352,12 +395,14 @@ def evaluate(U, I, data: OracleData, users, cfg: OracleConfig, is_val=False, fai
             lists = [rank_user_heapq(rate[j], data.train_items.get(u, []), data.n_items, kmax) for j, u in enumerate(blk)]
         else:
             lists = rank_users_numpy(rate, [data.train_items.get(u, []) for u in blk], kmax).tolist()
-        for u, top in zip(blk, lists):
+        for j, (u, top) in enumerate(zip(blk, lists)):
             pos = truth[u]
             r = [1 if i in pos else 0 for i in top]
             m = user_metrics(r, len(pos), Ks)
             for k in ("precision", "recall", "ndcg", "hit_ratio"):
                 res[k] += m[k] / n
+            if full:
+                res["auc"] += user_auc(rate[j], data.train_items.get(u, []), pos, data.n_items) / n
             tops[u] = top
     return res, tops
 
@@ -405,8 +450,8 @@ class OracleTrainer:
             n_inter += len(u)
         return dict(loss=tot, mf_loss=mf, emb_loss=emb, n_batch=n_batch, triplets=n_inter)
 
-    def test(self, users=None, is_val=False, faithful=True):
+    def test(self, users=None, is_val=False, faithful=True, full=False):
         with torch.no_grad():
             out = self.forward()
         users = list(self.data.test_set.keys()) if users is None else users
-        return evaluate(out["U"], out["I"], self.data, users, self.cfg, is_val, faithful)
+        return evaluate(out["U"], out["I"], self.data, users, self.cfg, is_val, faithful, full)

@@ -33,7 +33,8 @@ def main():
     lo, hi = b[rank], b[rank + 1]
     mine = e[(e[:, 0] >= lo) & (e[:, 0] < hi)]
     g = ShardedGraph(torch.from_numpy(mine[:, 0] - lo).to(dev), torch.from_numpy(mine[:, 1]).to(dev), hi - lo, ni, tile_nnz=32, pieces=(2 if world > 1 else 1))
-    sh = ShardedHotPath(g, Eu[lo:hi].clone().to(dev), Ei.clone().to(dev), cfg, lo, item_sharded=os.environ.get("LLMREC_DIST_ITEM_SHARDED") == "1")
+    sh = ShardedHotPath(g, Eu[lo:hi].clone().to(dev), Ei.clone().to(dev), cfg, lo, item_sharded=os.environ.get("LLMREC_DIST_ITEM_SHARDED") == "1",
+                        demand=os.environ.get("LLMREC_DIST_DEMAND") == "1")
     # reference: single-GPU engine on the full graph (every rank builds it; small)
     R = sp.csr_matrix((np.ones(len(e), np.float32), (e[:, 0], e[:, 1])), shape=(nu, ni))
     bg = BipartiteGraph(R, dev, tile_nnz=32)
@@ -47,9 +48,12 @@ def main():
         neg = torch.from_numpy(rng.integers(0, ni, 280).astype(np.int32)).to(dev)
         l1 = float(hp.train_step(users, pos, neg)); l2 = float(sh.train_step(users, pos, neg))
         ok &= abs(l1 - l2) < 1e-5 * max(1.0, abs(l1))
-        ok &= bool(torch.allclose(sh.U, hp.U[lo:hi], rtol=1e-4, atol=1e-6))
         rows = torch.cat([pos, neg]).long()           # the training step fuses I on the batch rows only
-        ok &= bool(torch.allclose(sh.I[rows], hp.I[rows], rtol=1e-4, atol=1e-6))
+        if sh.demand:                                 # ... and, in demand mode, U on the batch users only (compact blocks)
+            ok &= bool(torch.allclose(sh.Ub, hp.U[users.long()], rtol=1e-4, atol=1e-6)) and bool(torch.allclose(sh.Ib, hp.I[rows], rtol=1e-4, atol=1e-6))
+        else:
+            ok &= bool(torch.allclose(sh.U, hp.U[lo:hi], rtol=1e-4, atol=1e-6))
+            ok &= bool(torch.allclose(sh.I[rows], hp.I[rows], rtol=1e-4, atol=1e-6))
     hp.forward(); sh.forward()                        # full forward (eval form)
     ok &= bool(torch.allclose(sh.U, hp.U[lo:hi], rtol=1e-4, atol=1e-6)) and bool(torch.allclose(sh.I, hp.I, rtol=1e-4, atol=1e-6))
     ok &= bool(torch.allclose(sh.E_u, params["user_id_embedding.weight"][lo:hi], rtol=1e-4, atol=1e-6))

@@ -15,7 +15,17 @@ class CsrOperator:
         self.plan = plan if plan is not None else object()
         assert self.rowptr.numel() == self.n_rows + 1
 
-    def apply(self, segs):
+    def apply_rows(self, seg, rows, count, max_rows=None, src_mask=None):          # llmrec_spmm_rows_f32: listed rows only
+        X, Y, Z, sm = seg
+        full = torch.empty_like(Y)
+        self.apply([(X if src_mask is None else _masked_rows(X, src_mask), full, Z, sm)])
+        r = rows[:int(count[0])].long()
+        r = r[r >= 0]
+        Y[r] = full[r]
+
+    def apply(self, segs, src_mask=None):
+        if src_mask is not None:                         # clear bit = that source row is promised to be zero and must not be read
+            segs = [(_masked_rows(X, src_mask), Y, Z, sm) for X, Y, Z, sm in segs]
         rp = self.rowptr
         rows = torch.repeat_interleave(torch.arange(self.n_rows), rp[1:] - rp[:-1])
         e = torch.arange(int(rp[0]), int(rp[-1]))
@@ -33,6 +43,72 @@ class CsrOperator:
             if Z is not None:
                 acc = acc + Z
             Y.copy_(acc)
+
+
+def _bits(mask, n):
+    w = mask.to(torch.int64) & 0xffffffff
+    return ((w[:, None] >> torch.arange(32)) & 1).reshape(-1)[:n].bool()
+
+
+def _masked_rows(X, src_mask):
+    """poison the rows a source mask excludes: a correct kernel never reads them"""
+    keep = _bits(src_mask, X.shape[0])
+    return torch.where(keep[:, None], X, torch.full_like(X, float("nan"))).nan_to_num(0.0) if False else torch.where(keep[:, None], X, torch.zeros_like(X))
+
+
+class RowSet:                                            # llmrec_mark_neighbors / llmrec_mark_ids / llmrec_compact_mask
+    def __init__(self, n, device):
+        self.n = int(n)
+        self.mask = torch.zeros((self.n + 31) // 32 + 1, dtype=torch.int32)
+        self.list = torch.zeros(max(self.n, 1), dtype=torch.int32)
+        self.count = torch.zeros(1, dtype=torch.int32)
+        self._set = set()
+
+    def clear(self):
+        self._set = set(); self.mask.zero_(); self.count.zero_()
+
+    def _sync(self):
+        m = torch.zeros(self.mask.numel() * 32, dtype=torch.int64)
+        if self._set:
+            m[torch.tensor(sorted(self._set))] = 1
+        words = (m.view(-1, 32) << torch.arange(32)).sum(1)
+        self.mask.copy_(torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32))
+
+    def add_neighbors(self, rowptr, col, rows):
+        rp, c = rowptr.long(), col.long()
+        for r in rows.long().tolist():
+            if r >= 0:
+                self._set.update(c[rp[r]:rp[r + 1]].tolist())
+        self._sync()
+
+    def add_ids(self, ids):
+        self._set.update(i for i in ids.long().tolist() if i >= 0)
+        self._sync()
+
+    def compact(self):
+        ids = sorted(self._set, reverse=True)            # any order is allowed
+        self.list[:len(ids)] = torch.tensor(ids, dtype=torch.int32) if ids else torch.zeros(0, dtype=torch.int32)
+        self.count[0] = len(ids)
+
+
+def row_softmax_bwd_rows(S, dS, out, rows, count, max_rows=None):       # llmrec_row_softmax_bwd_rows_f32
+    r = rows[:int(count[0])].long()
+    out[r] = S[r] * (dS[r] - (S[r] * dS[r]).sum(-1, keepdim=True))
+    return out
+
+
+def zero_rows(Y, idx):                                   # llmrec_zero_rows_f32
+    i = idx.long()
+    Y[i[i >= 0]] = 0.0
+
+
+def assign_rows(G, idx, Y):                              # llmrec_assign_rows_f32
+    i = idx.long()
+    Y[i[i >= 0]] = G[i >= 0]
+
+
+def fill(t, v):                                          # llmrec_fill_f32
+    t.fill_(v)
 
 
 def row_scale_softmax(X, scale, out, softmax):           # llmrec_row_scale_softmax_f32
@@ -53,7 +129,14 @@ def _unit(x):
     return x / x.norm(dim=1, keepdim=True).clamp_min(1e-12)           # F.normalize(x, p=2, dim=1)
 
 
-def fuse_fwd(layers, sides, coefs, out, rows=None):      # llmrec_fuse_fwd_f32
+def fuse_fwd(layers, sides, coefs, out, rows=None, compact=False):      # llmrec_fuse_fwd_f32
+    if compact:                                          # layers at rows[b]; sides and out are compact [len(rows) x d] blocks
+        r = rows.long()
+        m = sum(l[r.clamp(min=0)] for l in layers) / len(layers)
+        for x, c in zip(sides, coefs):
+            m = m + c * _unit(x)
+        out.copy_(torch.where((r >= 0)[:, None], m, torch.zeros_like(m)))          # a negative entry = not mine: zeros
+        return out
     m = sum(layers) / len(layers)
     for x, c in zip(sides, coefs):
         m = m + c * _unit(x)
@@ -62,6 +145,23 @@ def fuse_fwd(layers, sides, coefs, out, rows=None):      # llmrec_fuse_fwd_f32
     else:
         out[rows.long()] = m[rows.long()]
     return out
+
+
+def rank1_add(blocks):                                   # llmrec_rank1_add_f32
+    for Y, sc, b in blocks:
+        Y += sc[:, None] * b[None, :]
+
+
+def scaled_colsum(terms, out, accumulate=False):         # llmrec_scaled_colsum_f32
+    t = sum(((G * sc[:, None]) if sc is not None else G).sum(0) for G, sc in terms)
+    out.copy_(out + t if accumulate else t)
+
+
+def feat_reg_gram(W, b, G, h, n2, c, dW, db, loss):      # llmrec_feat_reg_gram_f32
+    WG, Wh = W @ G, W @ h
+    loss += 0.5 * c * ((WG * W).sum() + 2 * (b * Wh).sum() + n2 * (b * b).sum())
+    dW += c * (WG + b[:, None] * h[None, :])
+    db += c * (Wh + n2 * b)
 
 
 def fuse_bwd(g, n_layers, d_layer, sides, coefs, d_sides, accumulate, rows=None):   # llmrec_fuse_bwd_f32
@@ -173,9 +273,11 @@ class AdamW:                                             # llmrec_adamw_advance 
         self.v = [torch.zeros_like(p) for p in self.params]
         self.t = 0
 
-    def step(self, grads):
+    def step(self, grads, row_masks=None):
         self.t += 1
         b1, b2 = self.betas
+        if row_masks is not None:                        # llmrec_adamw_step_rows_f32: g is read on the flagged rows only
+            grads = [g if mk is None else torch.where(_bits(mk, g.shape[0])[:, None], g, torch.zeros_like(g)) for g, mk in zip(grads, row_masks)]
         for p, g, m, v in zip(self.params, grads, self.m, self.v):
             p.mul_(1 - self.lr * self.wd)
             m.mul_(b1).add_(g, alpha=1 - b1)
@@ -191,8 +293,8 @@ def install():
     import llmrec_b200.dist as D
     me = sys.modules[__name__]
     import llmrec_b200.graph as G
-    for name in ("CsrOperator", "row_scale_softmax", "row_softmax_bwd", "fuse_fwd", "fuse_bwd", "gather_rows", "scatter_add_rows",
-                 "bpr_work", "bpr_heads", "grad_init", "AdamW", "proj_fwd_group", "proj_wgrad_group", "sqnorm_grad", "score_topk", "topk_hits"):
+    for name in ("CsrOperator", "RowSet", "row_softmax_bwd_rows", "zero_rows", "assign_rows", "fill", "row_scale_softmax", "row_softmax_bwd", "fuse_fwd", "fuse_bwd", "gather_rows", "scatter_add_rows",
+                 "bpr_work", "bpr_heads", "grad_init", "rank1_add", "scaled_colsum", "feat_reg_gram", "AdamW", "proj_fwd_group", "proj_wgrad_group", "sqnorm_grad", "score_topk", "topk_hits"):
         setattr(ops, name, getattr(me, name))
     D.CsrOperator = CsrOperator
     G.CsrOperator = CsrOperator

@@ -14,7 +14,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-NU, NI, D, L, B, STEPS, LR = 203, 96, 16, 2, 64, 3, 1e-2
+NU, NI, D, L, B, STEPS, LR = 203, 96, 32, 2, 64, 3, 1e-2
 
 
 def _problem():
@@ -65,7 +65,7 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _worker(rank, world, port, item_sharded, pieces, out):
+def _worker(rank, world, port, item_sharded, pieces, out, demand=False):
     sys.path.insert(0, HERE)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -81,8 +81,12 @@ def _worker(rank, world, port, item_sharded, pieces, out):
     lo, hi = b[rank], b[rank + 1]
     mine = e[(e[:, 0] >= lo) & (e[:, 0] < hi)]
     g = ShardedGraph(torch.from_numpy(mine[:, 0] - lo), torch.from_numpy(mine[:, 1]), hi - lo, NI, pieces=pieces)
-    sh = ShardedHotPath(g, Eu[lo:hi].clone(), Ei.clone(), cfg, lo, item_sharded=item_sharded)
-    assert sh.item_sharded == (item_sharded and world > 1)
+    sh = ShardedHotPath(g, Eu[lo:hi].clone(), Ei.clone(), cfg, lo, item_sharded=item_sharded, demand=demand)
+    assert sh.item_sharded == (item_sharded and world > 1) and sh.demand == demand
+    if demand:                                           # rows the demand mode never writes must not leak into results: poison them
+        for t in sh.Ul[1:] + sh.Il[1:]:
+            t.fill_(123.0)
+        sh.g_Eu.fill_(float("nan")); sh.bufU.fill_(float("nan"))
     sh.set_lr(LR)
     tol = dict(rtol=2e-4, atol=2e-6)
     ok = True
@@ -96,9 +100,10 @@ def _worker(rank, world, port, item_sharded, pieces, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,item_sharded,pieces", [(1, False, 1), (2, False, 1), (2, False, 2), (2, True, 1)])
-def test_sharded_engine_orchestration(world, item_sharded, pieces):
+@pytest.mark.parametrize("world,item_sharded,pieces,demand", [(1, False, 1, False), (2, False, 1, False), (2, False, 2, False), (2, True, 1, False),
+                                                               (1, False, 1, True), (2, False, 1, True), (2, False, 2, True)])
+def test_sharded_engine_orchestration(world, item_sharded, pieces, demand):
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), item_sharded, pieces, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), item_sharded, pieces, out, demand), nprocs=world, join=True)
     assert dict(out) == {r: True for r in range(world)}

@@ -15,6 +15,22 @@ def test_sharded_world1_equals_engine():
     assert "DIST_CHECK_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+def test_sharded_demand_world1_equals_engine():
+    """demand-driven step (last layer on the batch's neighbourhood only, row-sparse user gradient) == the dense single-GPU engine"""
+    r = subprocess.run([sys.executable, os.path.join(HERE, "dist_gpu_check.py")], capture_output=True, text=True, timeout=300,
+                       env=dict(os.environ, LLMREC_DIST_DEMAND="1"))
+    assert "DIST_CHECK_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_sharded_demand_world2_equals_engine():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29521", os.path.join(HERE, "dist_gpu_check.py")], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, LLMREC_DIST_DEMAND="1"))
+    assert "DIST_CHECK_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_sharded_world2_equals_engine():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")

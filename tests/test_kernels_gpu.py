@@ -372,3 +372,126 @@ def test_grad_init_regions():
     torch.testing.assert_close(odd, 0.5 * oddX, rtol=1e-6, atol=1e-9)
     want = c * 0.5 * float((wide[:, :128].double() ** 2).sum()) + 0.5 * 0.5 * float((oddX.double() ** 2).sum())
     assert abs(float(loss) - want) <= 1e-5 * want                            # overwritten, not accumulated
+
+
+def test_hoist_helpers_rank1_colsum_gram():
+    from llmrec_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    n, d, k = 700, 64, 96
+    T = torch.randn(n, k + 32, generator=g).to(cuda)                       # table with a scale column at k
+    Y = torch.randn(n, 3 * d, generator=g).to(cuda)
+    b = torch.randn(d, generator=g).to(cuda)
+    want = Y.clone(); want[:, d:2 * d] += T[:, k][:, None] * b[None, :]
+    ops.rank1_add([(Y[:, d:2 * d], T[:, k], b)])
+    torch.testing.assert_close(Y, want, rtol=1e-6, atol=1e-6)
+    G1, G2 = torch.randn(n, d, generator=g).to(cuda), torch.randn(2 * n, 2 * d, generator=g).to(cuda)
+    s2 = torch.randn(2 * n, generator=g).to(cuda)
+    out = torch.full((d,), 7.0, device=cuda)
+    for _ in range(2):                                                       # ticket reusable
+        ops.scaled_colsum([(G1, T[:, k]), (G2[:, d:], s2), (G1, None)], out, accumulate=False)
+    ref = (G1.double() * T[:, k].double()[:, None]).sum(0) + (G2[:, d:].double() * s2.double()[:, None]).sum(0) + G1.double().sum(0)
+    torch.testing.assert_close(out.double(), ref, rtol=1e-5, atol=1e-4)
+    ops.scaled_colsum([(G1, None)], out, accumulate=True)
+    torch.testing.assert_close(out.double(), ref + G1.double().sum(0), rtol=1e-5, atol=1e-4)
+    # feat_reg through the Gram matrix == the dense definition
+    X = torch.randn(900, k, generator=g).to(cuda); s = torch.rand(900, generator=g).to(cuda)
+    W = (torch.randn(d, k, generator=g) / k ** 0.5).to(cuda).requires_grad_(True)
+    bb = torch.randn(d, generator=g).to(cuda).requires_grad_(True)
+    c = 3e-4
+    F = X.double() @ W.double().t() + s.double()[:, None] * bb.double()[None, :]
+    L = c * 0.5 * (F ** 2).sum()
+    L.backward()
+    Gm = (X.double().t() @ X.double()).float(); h = (X.double().t() @ s.double()).float(); n2 = float((s.double() ** 2).sum())
+    dW = torch.ones(d, k, device=cuda); db = torch.ones(d, device=cuda); loss = torch.full((1,), 2.0, device=cuda)
+    for _ in range(1):
+        ops.feat_reg_gram(W.detach(), bb.detach(), Gm, h, n2, c, dW, db, loss)
+    torch.testing.assert_close(dW.double() - 1.0, W.grad.double(), rtol=2e-4, atol=1e-6)
+    torch.testing.assert_close(db.double() - 1.0, bb.grad.double(), rtol=2e-4, atol=1e-6)
+    assert abs(float(loss) - 2.0 - float(L)) <= 2e-4 * float(L) + 1e-6
+
+
+def test_fuse_fwd_compact_rows():
+    from llmrec_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    n, d, B = 500, 64, 77
+    layers = [torch.randn(n, d, generator=g).to(cuda) for _ in range(3)]
+    sides = [torch.randn(B, d, generator=g).to(cuda) for _ in range(2)]
+    rows = torch.randint(0, n, (B,), generator=g, dtype=torch.int32).to(cuda)
+    out = torch.empty(B, d, device=cuda)
+    ops.fuse_fwd(layers, sides, [0.02, 2.8], out, rows=rows, compact=True)
+    ref = sum(l[rows.long()] for l in layers) / 3 + 0.02 * torch.nn.functional.normalize(sides[0]) + 2.8 * torch.nn.functional.normalize(sides[1])
+    torch.testing.assert_close(out, ref, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("d", [32, 64, 128])
+def test_spmm_row_list_and_source_mask_match_the_full_product(d):
+    """llmrec_spmm_rows_f32 and the src_mask of llmrec_spmm_csr_f32 (the demand-driven step of dist.py): listed rows equal the
+    full product, unlisted rows are untouched, masked-out source rows are never read (they hold NaN), softmax / addend fused."""
+    import scipy.sparse as sp
+    from llmrec_b200 import ops
+    from llmrec_b200.graph import BipartiteGraph
+    rng = np.random.default_rng(d)
+    nu, ni, ne = 4001, 1500, 60000
+    w = 1.0 / (np.arange(ni) + 4.0); w /= w.sum()
+    R = sp.csr_matrix((np.ones(ne, np.float32), (rng.integers(0, nu, ne), rng.choice(ni, size=ne, p=w))), shape=(nu, ni))
+    R.sum_duplicates(); R.data[:] = 1.0
+    g = BipartiteGraph(R, cuda, tile_nnz=32)
+    gen = torch.Generator().manual_seed(d)
+    X = torch.randn(ni, d, generator=gen).to(cuda)
+    Z = torch.randn(nu, d, generator=gen).to(cuda)
+    full = torch.empty(nu, d, device=cuda)
+    for sm in (False, True):
+        g.ui.apply([(X, full, Z, sm)])
+        rs = ops.RowSet(nu, cuda)
+        items = torch.tensor(rng.integers(0, ni, 40).astype(np.int32)).to(cuda)
+        rs.clear(); rs.add_neighbors(g.rowptr_i, g.col_i, items); rs.add_ids(torch.tensor([5, -1, 7], dtype=torch.int32, device=cuda)); rs.compact()
+        n = int(rs.count[0])
+        want = set(np.concatenate([R[:, items.cpu().numpy()].nonzero()[0], [5, 7]]).tolist())
+        assert n == len(want) and set(rs.list[:n].cpu().tolist()) == want
+        out = torch.full((nu, d), 777.0, device=cuda)
+        g.ui.apply_rows((X, out, Z, sm), rs.list, rs.count)
+        listed = torch.zeros(nu, dtype=torch.bool, device=cuda); listed[rs.list[:n].long()] = True
+        torch.testing.assert_close(out[listed], full[listed], rtol=1e-5, atol=1e-6)
+        assert bool((out[~listed] == 777.0).all())
+    # source mask: rows of the operand outside the set hold NaN and must never be fetched
+    Y = torch.randn(nu, d, generator=gen).to(cuda)
+    keep = torch.zeros(nu, dtype=torch.bool, device=cuda); keep[rs.list[:n].long()] = True
+    Yz = torch.where(keep[:, None], Y, torch.zeros_like(Y))
+    Yn = torch.where(keep[:, None], Y, torch.full_like(Y, float("nan")))
+    ref, got = torch.empty(ni, d, device=cuda), torch.empty(ni, d, device=cuda)
+    g.uiT.apply([(Yz, ref, None, False)])
+    g.uiT.apply([(Yn, got, None, False)], src_mask=rs.mask)
+    assert bool(torch.isfinite(got).all())
+    torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-6)
+    # row-list softmax backward, zero / assign rows
+    S = torch.softmax(torch.randn(nu, d, generator=gen).to(cuda), -1); dS = torch.randn(nu, d, generator=gen).to(cuda)
+    o = torch.full((nu, d), 3.0, device=cuda)
+    ops.row_softmax_bwd_rows(S, dS, o, rs.list, rs.count)
+    torch.testing.assert_close(o[keep], (S * (dS - (S * dS).sum(-1, keepdim=True)))[keep], rtol=1e-5, atol=1e-6)
+    assert bool((o[~keep] == 3.0).all())
+    idx = torch.tensor([3, -1, 9, 3], dtype=torch.int32, device=cuda)
+    ops.zero_rows(o, idx)
+    assert float(o[3].abs().sum()) == 0.0 and float(o[9].abs().sum()) == 0.0 and float(o[4].abs().sum()) > 0
+    G = torch.arange(4 * d, dtype=torch.float32, device=cuda).view(4, d); G[3] = G[0]
+    ops.assign_rows(G, idx, o)
+    assert torch.equal(o[3], G[0]) and torch.equal(o[9], G[2])
+
+
+def test_adamw_row_sparse_gradient_matches_dense():
+    from llmrec_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    n, w = 1000, 64
+    p0 = torch.randn(n, w, generator=g).to(cuda)
+    small = torch.randn(17, 8, generator=g).to(cuda)
+    rows = torch.tensor([0, 5, 999, 31, 32, 63, 64], dtype=torch.int32, device=cuda)
+    rs = ops.RowSet(n, cuda)
+    a, b = ops.AdamW([p0.clone(), small.clone()], lr=1e-3), ops.AdamW([p0.clone(), small.clone()], lr=1e-3)
+    for step in range(4):
+        gd = torch.zeros(n, w, device=cuda); gd[rows.long()] = torch.randn(rows.numel(), w, generator=g).to(cuda)
+        gs = torch.randn(17, 8, generator=g).to(cuda)
+        gsparse = torch.where((gd != 0).any(1, keepdim=True), gd, torch.full_like(gd, float("nan")))   # rows without a gradient are never read
+        rs.clear(); rs.add_ids(rows)
+        a.step([gd, gs])
+        b.step([gsparse, gs], row_masks=[rs.mask, None])
+    for x, y in zip(a.params + a.m + a.v, b.params + b.m + b.v):
+        assert torch.equal(x, y)

@@ -87,11 +87,13 @@ def test_fused_step_grads_match_reference(tiny_root, golden, mode):
         np.testing.assert_allclose(gten.cpu().numpy(), ref, rtol=2e-3, atol=1e-9 + 2e-5 * np.abs(ref).max(), err_msg=name)
 
 
-@pytest.mark.parametrize("mode,graph", [("3xtf32", 1), ("fp32", 1), ("3xtf32", 0)])
-def test_epoch_matches_reference_golden(tiny_root, golden, mode, graph):
+@pytest.mark.parametrize("mode,graph,hoist", [("3xtf32", 1, 0), ("fp32", 1, 0), ("3xtf32", 0, 0), ("3xtf32", 1, 1), ("3xtf32", 0, 1)])
+def test_epoch_matches_reference_golden(tiny_root, golden, mode, graph, hoist):
     """Same seed, same sampler stream, 8 steps of AdamW, then full-catalog eval: params, epoch loss, metrics, hit vectors.
-    graph=1 replays the step from a CUDA graph (the default), graph=0 launches eagerly."""
-    tr, gen, M = _trainer(tiny_root, ["--proj_mode", mode, "--cuda_graph", str(graph)])
+    graph=1 replays the step from a CUDA graph (the default), graph=0 launches eagerly; hoist=1 is the hoisted side-feature
+    engine (hoist.py), held to the SAME golden tolerances as the default engine."""
+    tr, gen, M = _trainer(tiny_root, ["--proj_mode", mode, "--cuda_graph", str(graph), "--hoist_side", str(hoist)])
+    assert tr.hoisted == bool(hoist)
     M.set_seed(2022)
     logs = []
     tr.logger.logging = lambda s: logs.append(str(s))
@@ -231,3 +233,90 @@ def test_graphed_steps_with_varying_batch_length_match_eager(tiny_root):
             torch.testing.assert_close(sg[k], se[k], rtol=2e-5, atol=2e-7)
     for t in junk:
         assert float(t[0]) == float(t[-1])                                          # nothing scribbled over live memory
+
+
+def test_hoisting_switches_itself_off_when_dropout_or_mask_is_on(tiny_root):
+    """The linearity argument of hoist.py needs Dropout to be the identity: --drop_rate > 0 (or the mask branch) falls back to the default engine."""
+    tr, gen, M = _trainer(tiny_root, ["--hoist_side", "1", "--drop_rate", "0.2"])
+    assert tr.hoisted is False and type(tr.hot).__name__ == "HotPath"
+
+
+def test_hoisted_step_matches_default_engine_on_the_same_batches(tiny_root):
+    """Default vs hoisted engine, same init, same batches, 6 steps: losses, every parameter, and the eval forward agree to fp32
+    reassociation level (tighter than the golden tolerances)."""
+    a, gen, M = _trainer(tiny_root, ["--cuda_graph", "0"])
+    b, _, _ = _trainer(tiny_root, ["--cuda_graph", "1", "--hoist_side", "1"])
+    M.set_seed(5)
+    for i in range(6):
+        u, p, n = a.sample_batch()
+        la, lb = float(a.train_batch(u, p, n)), float(b.train_batch(u, p, n))
+        assert abs(la - lb) <= 2e-5 * max(1.0, abs(la)), (i, la, lb)
+    sa, sb = a.model_mm.state_dict(), b.model_mm.state_dict()
+    for k in sa:
+        if not k.startswith("batch_norm"):
+            torch.testing.assert_close(sb[k], sa[k], rtol=1e-4, atol=1e-6, msg=k)
+    Ua, Ia = a.hot.forward(); Ub, Ib = b.hot.forward()
+    torch.testing.assert_close(Ub, Ua, rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(Ib, Ia, rtol=1e-4, atol=1e-6)
+
+
+def test_full_test_flag_auc_matches_sklearn_oracle(tiny_root):
+    """--test_flag full (batch_test.py:38-68): same hit-based metrics plus the per-user ROC-AUC over every candidate, against the
+    oracle's sklearn.roc_auc_score on the same embeddings."""
+    from oracle import llmrec_oracle as O
+    tr, gen, M = _trainer(tiny_root, ["--test_flag", "full"])
+    M.set_seed(3)
+    for _ in range(3):
+        tr.train_batch(*tr.sample_batch())
+    users = list(gen.test_set.keys())
+    res = tr.test(users, is_val=False)
+    data = O.load_dataset(gen.path if hasattr(gen, "path") else os.path.join(tiny_root, "netflix_valid_item"))
+    U, I = tr.hot.U.cpu(), tr.hot.I.cpu()
+    ores, _ = O.evaluate(U, I, data, users, O.OracleConfig(batch_size=128), is_val=False, faithful=True, full=True)
+    assert res["auc"] > 0.3 and abs(res["auc"] - ores["auc"]) < 1e-5, (res["auc"], ores["auc"])
+    for k in ("recall", "ndcg", "precision", "hit_ratio"):
+        np.testing.assert_allclose(res[k], ores[k], atol=1e-4)
+
+
+def test_mask_dropout_restoration_branch_matches_oracle(tiny_root):
+    """--mask 1 --mask_rate 0.1 --drop_rate 0.2 --att_re_rate 0.5 (Models.py:131-150, main.py:258-271): the eager optional branch of
+    Trainer against the oracle's autograd on the same state -- identical torch.randperm draws (CPU generator state copied), the
+    dropout masks the GPU step drew, the same Decoder weights."""
+    from oracle import llmrec_oracle as O
+    flags = ["--mask", "1", "--mask_rate", "0.1", "--drop_rate", "0.2", "--att_re_rate", "0.5", "--cuda_graph", "1", "--hoist_side", "1"]
+    tr, gen, M = _trainer(tiny_root, flags)
+    assert tr.masked_mode and not tr.hoisted
+    data = O.load_dataset(os.path.join(tiny_root, "netflix_valid_item"))
+    cfg = O.OracleConfig(batch_size=128)
+    otr = O.OracleTrainer(data, cfg)
+    sd = tr.model_mm.state_dict()
+    with torch.no_grad():
+        for k in O.PARAM_NAMES:
+            otr.params[k].copy_(sd[k].cpu())
+    m = tr.model_mm
+    otr.feats = dict(image=m.image_feats.cpu().clone(), text=m.text_feats.cpu().clone(), user=m.user_feats.cpu().clone(),
+                     item={k: v.cpu().clone() for k, v in m.item_feats.items()})
+    dec = dict(u_w=tr.decoder.u_net[0].weight.detach().cpu(), u_b=tr.decoder.u_net[0].bias.detach().cpu(),
+               i_w=tr.decoder.i_net[0].weight.detach().cpu(), i_b=tr.decoder.i_net[0].bias.detach().cpu())
+    raw_u = torch.tensor(tr.user_init_embedding).float()
+    raw_i = {k: torch.tensor(v).float() for k, v in tr.item_attribute_embedding.items()}
+    M.set_seed(9)
+    for step in range(2):
+        users, pos, neg = tr.sample_batch()
+        state = torch.get_rng_state()
+        got = float(tr.train_batch(users, pos, neg))
+        torch.set_rng_state(state)                                    # the oracle draws the same permutations
+        i_mask, u_mask = O.mask_features(otr.feats, data.n_users, data.n_items, True, 0.1)
+        drop = [mk.cpu() for mk in tr._last_dropout_masks]
+        assert 0.7 < float(drop[0].gt(0).float().mean()) < 0.9 and abs(float(drop[0].max()) - 1.25) < 1e-6
+        out = O.forward(otr.params, otr.feats, otr.ui, otr.iu, cfg, drop=drop)
+        total, _ = O.batch_loss(out, users, pos, neg, data.n_items, cfg)
+        total = total + 0.5 * O.restoration_loss(out, dec, raw_u, raw_i, i_mask, u_mask, alpha=2, kind="sce")
+        otr.opt.zero_grad(); total.backward(); otr.opt.step()
+        assert abs(got - float(total)) <= 5e-5 * max(1.0, abs(float(total))), (step, got, float(total))
+        torch.testing.assert_close(m.user_feats.cpu(), otr.feats["user"], rtol=1e-6, atol=1e-6)           # same rows were overwritten
+    sd = tr.model_mm.state_dict()
+    for k in O.PARAM_NAMES:
+        np.testing.assert_allclose(sd[k].cpu().numpy(), otr.params[k].detach().numpy(), rtol=3e-4, atol=3e-6, err_msg=k)
+    res = tr.test(list(gen.test_set.keys()), is_val=False)          # eval keeps masking (Models.py:131-142 is unconditional)
+    assert np.isfinite(res["recall"]).all()

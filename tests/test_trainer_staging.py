@@ -31,8 +31,11 @@ class _Hot:
     def __init__(self, batch):
         self.batch, self.buf = batch, None
 
+    def batch_capacity(self):
+        return (self.batch + int(self.batch * 0.1) + 7) // 8 * 8
+
     def index_buffer(self, need):
-        need = max(int(need), 2 * self.batch)
+        need = max(int(need), self.batch_capacity())
         if self.buf is None or self.buf.shape[1] < need:
             self.buf = torch.zeros((4, need), dtype=torch.int32)
         return self.buf
