@@ -169,16 +169,21 @@ def time_e2e(tr, K, min_seconds, max_blocks):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     blocks, spent, per_step = [], 0.0, []
+    dev_sampler = getattr(tr, "device_sampler", None) is not None
     while True:
         torch.cuda.synchronize()
         n_e2e = h2d = 0
+        n0 = float(tr._epoch_stats[3]) if dev_sampler else 0.0
         e0.record()
         for i in range(K):
             loss, B = tr.train_next_batch()          # the body of Trainer.train()'s loop: host sampler -> pinned staging -> H2D -> step
             loss_host[i:i + 1].copy_(loss, non_blocking=True)
-            n_e2e += B; h2d += tr.last_h2d_bytes
+            if not dev_sampler:
+                n_e2e += B; h2d += tr.last_h2d_bytes
         e1.record()
         torch.cuda.synchronize()
+        if dev_sampler:                              # batches drawn on the device: B' is accumulated there, nothing crosses PCIe but the loss
+            n_e2e = int(float(tr._epoch_stats[3]) - n0)
         ms = e0.elapsed_time(e1)
         assert bool(torch.isfinite(loss_host).all()), "non-finite loss"
         blocks.append(ms); spent += ms; per_step.append((n_e2e / (ms / 1e3), h2d // K))
@@ -233,11 +238,11 @@ def eval_leg(tr, gen, ni, shots=5):
             "recall@20": float(res["recall"][1]), "ndcg@20": float(res["ndcg"][1]), "includes": "forward + scoring + top-50 + metrics, host buffers"}
 
 
-def run_workload(name, a, K, W, min_seconds, with_families=True, hoist=False):
+def run_workload(name, a, K, W, min_seconds, with_families=True, hoist=False, extra=()):
     """One single-GPU configuration: device-resident leg, e2e leg, family roofline, eval leg."""
     import torch
     from llmrec_b200.roofline import peaks, step_bytes
-    tr, gen, args = make_trainer(name, a, extra=(["--hoist_side", "1"] if hoist else []))
+    tr, gen, args = make_trainer(name, a, extra=(["--hoist_side", "1"] if hoist else []) + list(extra))
     ds, nu, ni, ne, dims, embed, wsize = WORKLOADS[name]
     t = time_steps(tr, a, K, W, min_seconds, a.max_blocks)
     e2e = time_e2e(tr, K, min_seconds / 2, a.max_blocks)
@@ -406,6 +411,13 @@ def run_ours(a):
             torch.cuda.empty_cache()
         except Exception as e:                                        # an extra leg must never take the headline down
             cfgs[a.workload + "_hoisted"] = {"error": repr(e)[:300]}
+        try:
+            dsm, _, _ = run_workload(a.workload, a, K, W, min(a.min_seconds, 1.0), with_families=False, hoist=True, extra=["--device_sampler", "1"])
+            cfgs[a.workload + "_hoisted_device_sampler"] = dict(dsm, note="--hoist_side 1 --device_sampler 1: batches drawn on the GPU inside the replayed graph "
+                                                                "(SURVEY.md 8f-1; same distributions, not the reference's RNG streams); e2e moves no index bytes")
+            torch.cuda.empty_cache()
+        except Exception as e:
+            cfgs[a.workload + "_hoisted_device_sampler"] = {"error": repr(e)[:300]}
         other = "movielens" if a.workload == "netflix" else "netflix"
         try:
             m, _, _ = run_workload(other, a, K, W, min(a.min_seconds, 1.0))

@@ -292,6 +292,18 @@ int llmrec_host_sample_batch(uint32_t* py_key, int32_t* py_pos, uint32_t* np_key
                              int32_t n_aug_table, int32_t aug_limit, int32_t* stamp, int32_t epoch, int32_t* pool,
                              int32_t* out, int64_t ld, int32_t* n_out);
 
+/* Device-side batch sampler (utility/load_data.py:157-195 + main.py:216-224 on the GPU): ONE kernel fills the [4 x cap]
+ * int32 index buffer of a training step -- rows users / pos / neg and the meta row {B', n_keep} looked up in meta_table[2*B' ..] -- from
+ * DEVICE copies of exist_users, the train CSR (rows SORTED ascending) and the augmented-edge tables (ids < 0 or >= aug_limit are dropped,
+ * as upstream's filter does; INT32_MIN = uid missing).  state = device uint64[2] {seed, step}; the kernel advances `step`, so the launch
+ * can live inside a captured CUDA graph.  NOT bit-compatible with the reference's host RNG streams (that is llmrec_host_sample_batch, the
+ * default): same distributions, counter-based generator.  key_scratch: uint32[max(n_exist, batch)]. */
+int llmrec_device_sample_batch(const int32_t* exist_users, int32_t n_exist, int32_t batch,
+                               const int32_t* train_rowptr, const int32_t* train_col, int32_t n_items,
+                               int32_t n_aug, const int32_t* aug_pos, const int32_t* aug_neg, int32_t n_aug_table, int32_t aug_limit,
+                               const int32_t* meta_table, int32_t cap, uint64_t* state, int32_t* out, uint32_t* key_scratch,
+                               llmrec_stream_t stream);
+
 /* Row helpers of the sharded (multi-GPU) path: epilogue of an item-side propagation applied AFTER the cross-rank
  * sum of per-rank partials, and gather / scatter-add of batch rows by index (idx < 0 = row not owned: zeros / skipped). */
 int llmrec_row_scale_softmax_f32(const float* X, int64_t ldx, const float* scale, float* Y, int64_t ldy, int64_t n, int32_t d,
@@ -309,7 +321,8 @@ int llmrec_scatter_add_rows_f32(const float* G, int64_t ldg, const int32_t* idx,
  *   scaled_colsum  out[c] (+)= sum_terms sum_r scale[r * lds] * G[r * ldg + c]   (bias gradient; scale == NULL means 1)
  *   feat_reg_gram  feat_reg (main.py:151-156) over ALL rows through the k x k Gram matrix of a propagated table X~ and
  *                  h = X~^T s, n2 = |s|^2:  loss += c/2 (tr(W G W^T) + 2 b^T W h + n2 |b|^2);  dW += c (W G + b h^T);
- *                  db += c (W h + n2 b).  scratch: d + 4 floats zeroed once (ticket re-zeroed by the kernel).
+ *                  db += c (W h + n2 b).  Two launches: W G by the exact-fp32 SIMT GEMM, then one pass over [d x k].
+ *                  scratch: llmrec_feat_reg_gram_scratch(d, k) floats, zeroed once (ticket re-zeroed by the kernel).
  * --------------------------------------------------------------------------------------------- */
 typedef struct { float* Y; const float* scale; const float* bias; int64_t ldy, lds, n; int32_t width, _pad; } llmrec_rank1_block;
 typedef struct { const float* G; const float* scale; int64_t ldg, lds, n; } llmrec_colsum_term;
@@ -319,6 +332,7 @@ int llmrec_scaled_colsum_f32(const llmrec_colsum_term* terms_host, int32_t n_ter
 int64_t llmrec_scaled_colsum_scratch(int32_t width);
 int llmrec_feat_reg_gram_f32(const float* W, const float* bias, const float* G, const float* h, float n2, int32_t d, int32_t k, float c,
                              float* dW, float* db, float* loss_accum, float* scratch, llmrec_stream_t stream);
+int64_t llmrec_feat_reg_gram_scratch(int32_t d, int32_t k);
 
 /* small utilities used by the host mirror */
 int llmrec_fill_f32(float* p, int64_t n, float v, llmrec_stream_t stream);

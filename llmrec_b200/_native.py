@@ -108,6 +108,8 @@ SIGNATURES = {
     "llmrec_host_sample_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                            C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                            C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "llmrec_device_sample_batch": (C.c_int, [c_i32p, C.c_int32, C.c_int32, c_i32p, c_i32p, C.c_int32, C.c_int32, c_i32p, c_i32p, C.c_int32, C.c_int32,
+                                             c_i32p, C.c_int32, C.c_void_p, c_i32p, C.c_void_p, c_stream]),
     "llmrec_row_scale_softmax_f32": (C.c_int, [c_f32p, C.c_int64, c_f32p, c_f32p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, c_stream]),
     "llmrec_gather_rows_f32": (C.c_int, [c_f32p, C.c_int64, c_i32p, C.c_int32, C.c_int32, c_f32p, C.c_int64, c_stream]),
     "llmrec_scatter_add_rows_f32": (C.c_int, [c_f32p, C.c_int64, c_i32p, C.c_int32, C.c_int32, c_f32p, C.c_int64, c_stream]),
@@ -115,6 +117,7 @@ SIGNATURES = {
     "llmrec_scaled_colsum_f32": (C.c_int, [C.POINTER(ColsumTerm), C.c_int32, C.c_int32, c_f32p, C.c_int32, c_f32p, c_stream]),
     "llmrec_scaled_colsum_scratch": (C.c_int64, [C.c_int32]),
     "llmrec_feat_reg_gram_f32": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_float, C.c_int32, C.c_int32, C.c_float, c_f32p, c_f32p, c_f32p, c_f32p, c_stream]),
+    "llmrec_feat_reg_gram_scratch": (C.c_int64, [C.c_int32, C.c_int32]),
     "llmrec_fill_f32": (C.c_int, [c_f32p, C.c_int64, C.c_float, c_stream]),
     "llmrec_panelize_f32": (C.c_int, [c_f32p, C.c_int64, C.c_int64, C.c_int32, c_f32p, c_stream]),
 }

@@ -94,11 +94,18 @@ __device__ void bpr_select_head(const BprParams& p, int h, int B, int n_keep) {
         if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1);
       }
       __syncthreads();
-      if (tid == 0) {
-        int want = s_want, bin = 0;
-        while (bin < 255 && want >= hist[bin]) { want -= hist[bin]; ++bin; }
-        s_want = want;
-        s_prefix = prefix | ((unsigned)bin << shift);
+      {  // which bin holds rank `want`: exclusive scan of the 256 counts (one per thread), the owning thread publishes bin and remainder
+        const int cnt = hist[tid], lane = tid & 31, wp = tid >> 5;
+        int inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) redi[wp] = inc;
+        __syncthreads();
+        int before = inc - cnt;
+        for (int q = 0; q < wp; ++q) before += redi[q];
+        const int want = s_want;
+        __syncthreads();
+        if (cnt > 0 && before <= want && want < before + cnt) { s_want = want - before; s_prefix = prefix | ((unsigned)tid << shift); }
       }
       __syncthreads();
     }

@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(256) rank1_add_kernel(const Rank1Params p) {
 }
 
 struct ColsumParams { llmrec_colsum_term term[kMaxBlocks]; int n_terms; int width; float* out; int accumulate; float* partial; unsigned* ticket; };
-constexpr int kColsumSlices = 32;
+constexpr int kColsumSlices = 128;
 
 // out[c] (+)= sum over terms, rows of scale[r] * G[r, c]; grid (ceil(width/32), kColsumSlices): warp w of a CTA takes rows w, w+8.. of its slice,
 // partials are combined in a fixed order by the last CTA of each column group (deterministic)
@@ -38,10 +38,19 @@ __global__ void __launch_bounds__(256) scaled_colsum_kernel(const ColsumParams p
   float acc = 0.f;
   for (int t = 0; t < p.n_terms; ++t) {
     const llmrec_colsum_term tm = p.term[t];
-    for (int64_t r = (int64_t)blockIdx.y * 8 + w; r < tm.n; r += (int64_t)kColsumSlices * 8) {
-      const float s = tm.scale ? __ldg(tm.scale + r * tm.lds) : 1.0f;
-      if (c < p.width) acc = fmaf(s, tm.G[r * tm.ldg + c], acc);
+    const int64_t st = (int64_t)kColsumSlices * 8;
+    int64_t r = (int64_t)blockIdx.y * 8 + w;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;                       // independent chains: the loads of 4 rows are in flight together
+    if (c < p.width) {
+      for (; r + 3 * st < tm.n; r += 4 * st) {
+        const float s0 = tm.scale ? __ldg(tm.scale + r * tm.lds) : 1.0f, s1 = tm.scale ? __ldg(tm.scale + (r + st) * tm.lds) : 1.0f;
+        const float s2 = tm.scale ? __ldg(tm.scale + (r + 2 * st) * tm.lds) : 1.0f, s3 = tm.scale ? __ldg(tm.scale + (r + 3 * st) * tm.lds) : 1.0f;
+        a0 = fmaf(s0, tm.G[r * tm.ldg + c], a0); a1 = fmaf(s1, tm.G[(r + st) * tm.ldg + c], a1);
+        a2 = fmaf(s2, tm.G[(r + 2 * st) * tm.ldg + c], a2); a3 = fmaf(s3, tm.G[(r + 3 * st) * tm.ldg + c], a3);
+      }
+      for (; r < tm.n; r += st) a0 = fmaf(tm.scale ? __ldg(tm.scale + r * tm.lds) : 1.0f, tm.G[r * tm.ldg + c], a0);
     }
+    acc += (a0 + a1) + (a2 + a3);
   }
   red[w][lane] = acc;
   __syncthreads();
@@ -65,28 +74,24 @@ __global__ void __launch_bounds__(256) scaled_colsum_kernel(const ColsumParams p
   if (threadIdx.x == 0) p.ticket[blockIdx.x] = 0u;
 }
 
-// One CTA per row i of W[d x k]:  dW[i,:] += c (W[i,:] G + b_i h^T);  db_i += c (W[i,:].h + n2 b_i);
-// loss += c/2 (W[i,:] G W[i,:]^T + 2 b_i W[i,:].h + n2 b_i^2) summed over i in a fixed order by the last CTA.
-__global__ void __launch_bounds__(256) feat_reg_gram_kernel(const float* __restrict__ W, const float* __restrict__ b, const float* __restrict__ G,
-                                                            const float* __restrict__ h, float n2, int d, int k, float c,
-                                                            float* dW, float* db, float* loss, float* partial, unsigned* ticket) {
-  extern __shared__ float wrow[];   // k floats
+// Second half of feat_reg_gram: WG = W G was formed by the exact-fp32 SIMT GEMM (proj_fwd_simt: Y = X W'^T with X = W, W' = G = G^T).
+// One CTA per row i of W[d x k]:  dW[i,:] += c (WG[i,:] + b_i h^T);  db_i += c (W[i,:].h + n2 b_i);
+// loss += c/2 (WG[i,:].W[i,:] + 2 b_i W[i,:].h + n2 b_i^2) summed over i in a fixed order by the last CTA.
+__global__ void __launch_bounds__(256) feat_reg_finish_kernel(const float* __restrict__ W, const float* __restrict__ b, const float* __restrict__ WG,
+                                                              const float* __restrict__ h, float n2, int d, int k, float c,
+                                                              float* dW, float* db, float* loss, float* partial, unsigned* ticket) {
   __shared__ float red[32];
   __shared__ bool s_last;
   const int i = blockIdx.x;
-  for (int j = threadIdx.x; j < k; j += blockDim.x) wrow[j] = W[(size_t)i * k + j];
-  __syncthreads();
   const float bi = b ? b[i] : 0.f;
   float quad = 0.f, wh = 0.f;
   for (int j = threadIdx.x; j < k; j += blockDim.x) {
-    float a = 0.f;
-    for (int l = 0; l < k; ++l) a = fmaf(wrow[l], __ldg(G + (size_t)l * k + j), a);     // (W G)_{ij}; G is symmetric, row l read coalesced over j
+    const float w = W[(size_t)i * k + j], a = WG[(size_t)i * k + j];
     const float hj = h ? __ldg(h + j) : 0.f;
-    quad = fmaf(a, wrow[j], quad);
-    wh = fmaf(wrow[j], hj, wh);
+    quad = fmaf(a, w, quad);
+    wh = fmaf(w, hj, wh);
     dW[(size_t)i * k + j] += c * (a + bi * hj);
   }
-  // block sums (fixed tree)
   auto bsum = [&](float v) {
     v = warp_sum(v);
     __syncthreads();
@@ -113,6 +118,7 @@ __global__ void __launch_bounds__(256) feat_reg_gram_kernel(const float* __restr
     *ticket = 0u;
   }
 }
+int proj_fwd_simt(const float*, int64_t, const float*, const float*, float*, int64_t, int64_t, int, int, cudaStream_t);
 }  // namespace llmrec
 
 using namespace llmrec;
@@ -149,16 +155,17 @@ extern "C" int llmrec_scaled_colsum_f32(const llmrec_colsum_term* terms, int32_t
   return 0;
 }
 
+extern "C" int64_t llmrec_feat_reg_gram_scratch(int32_t d, int32_t k) { return (int64_t)d * k + d + 4; }
+
 extern "C" int llmrec_feat_reg_gram_f32(const float* W, const float* bias, const float* G, const float* h, float n2, int32_t d, int32_t k, float c,
                                         float* dW, float* db, float* loss_accum, float* scratch, llmrec_stream_t stream) {
   LLMREC_REQUIRE_DEVICE();
-  LLMREC_CHECK_ARG(d >= 1 && d <= 1024 && k >= 1 && (size_t)k * 4 <= 160 * 1024, "feat_reg_gram: d=%d k=%d out of range", d, k);
-  const size_t smem = (size_t)k * sizeof(float);
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(feat_reg_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    LLMREC_CHECK_ARG(e == cudaSuccess, "feat_reg_gram: cannot reserve %zu bytes of shared memory", smem);
-  }
-  feat_reg_gram_kernel<<<d, 256, smem, as_stream(stream)>>>(W, bias, G, h, n2, d, k, c, dW, db, loss_accum, scratch, reinterpret_cast<unsigned*>(scratch + d));
-  LLMREC_CHECK_LAUNCH("feat_reg_gram");
+  LLMREC_CHECK_ARG(d >= 1 && k >= 1 && scratch, "feat_reg_gram: d=%d k=%d out of range", d, k);
+  cudaStream_t st = as_stream(stream);
+  float* WG = scratch + d + 4;                                    // [d x k] after the partial/ticket block
+  int rc = proj_fwd_simt(W, k, G, nullptr, WG, k, d, k, k, st);   // WG = W G^T = W G (G symmetric): exact fp32, 64 x 64 tiles
+  if (rc) return rc;
+  feat_reg_finish_kernel<<<d, 256, 0, st>>>(W, bias, WG, h, n2, d, k, c, dW, db, loss_accum, scratch, reinterpret_cast<unsigned*>(scratch + d));
+  LLMREC_CHECK_LAUNCH("feat_reg_finish");
   return 0;
 }

@@ -544,6 +544,8 @@ int proj_fwd_tc_group(const llmrec_proj_fwd_problem* pr, int n_prob, int d, int 
   P.total_tiles = tiles;
   static const bool krot = getenv("LLMREC_PROJ_KROT") != nullptr;
   P.krot = krot ? 1 : 0;
+  static const bool skipw = getenv("LLMREC_PROJ_SKIPW") != nullptr;
+  P.skipw = skipw ? 1 : 0;
   uint32_t smem;
   P.stages = stages_for(d, split, &smem);
   P.tmem_cols = (int)pow2_cols(2 * d);

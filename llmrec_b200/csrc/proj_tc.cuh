@@ -17,6 +17,7 @@ struct FwdParams {
   FwdProblem prob[kMaxProb];
   int n_prob, total_tiles, d, stages, tmem_cols;
   int wbox;   // experiment (LLMREC_PROJ_WBOX): W_hi and W_lo of a k-block arrive as ONE [2d x 32] TMA box (they are adjacent rows of the split matrix and adjacent in the stage)
+  int skipw;  // TIMING experiment only (LLMREC_PROJ_SKIPW, results are wrong): the W tiles are not fetched, isolating the L2->SM cost of re-reading W per k-block
   int krot;   // experiment (LLMREC_PROJ_KROT): CTA b starts its k loop at block b mod kblocks, so concurrent CTAs read different columns
 };
 

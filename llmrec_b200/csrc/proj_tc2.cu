@@ -68,13 +68,15 @@ __global__ void __launch_bounds__(512, 1) proj_fwd_ts_kernel(const __grid_consta
       const int kb_n = P.prob[p].kblocks;
       for (int kb = 0; kb < kb_n; ++kb) {
         mbar_wait(&empty[st.stage], st.phase ^ 1);
-        mbar_arrive_expect_tx(&full[st.stage], stage_bytes);
+        mbar_arrive_expect_tx(&full[st.stage], P.skipw ? kTileA : stage_bytes);
         // panels: tile (panel kb, rows mblk*BM..) is one contiguous 16 KiB run (panels are zero-padded to a multiple of 128 rows)
         const int kbe = P.krot ? (kb + (int)blockIdx.x) % kb_n : kb;   // which k-block this stage holds (the sum over k is order-free)
         if (P.prob[p].panel) tma_load_2d(sA(st.stage), &P.tmA[p], &full[st.stage], 0, kbe * P.prob[p].panel + mblk * BM);
         else tma_load_2d(sA(st.stage), &P.tmA[p], &full[st.stage], kbe * BK, mblk * BM);
-        tma_load_2d(sB(st.stage), &P.tmW[p], &full[st.stage], kbe * BK, 0);      // wbox: this one box is [2d x 32] = W_hi | W_lo
-        if (!P.wbox) tma_load_2d(sBlo(st.stage), &P.tmW[p], &full[st.stage], kbe * BK, d);
+        if (!P.skipw) {
+          tma_load_2d(sB(st.stage), &P.tmW[p], &full[st.stage], kbe * BK, 0);      // wbox: this one box is [2d x 32] = W_hi | W_lo
+          if (!P.wbox) tma_load_2d(sBlo(st.stage), &P.tmW[p], &full[st.stage], kbe * BK, d);
+        }
         st.advance();
       }
     }

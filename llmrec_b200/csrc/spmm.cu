@@ -20,6 +20,7 @@
 //     and the store are fused at the row boundary.
 #include <stdlib.h>
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace llmrec {
 
@@ -174,6 +175,106 @@ __global__ void __launch_bounds__(256, MINB) spmm_tile_kernel(const SpmmParams p
     }
   } else {
     for (; cur < nrows; ++cur) finish_row<CH>(p, lc, acc, row0 + cur, gmask);  // last row and trailing empty rows
+  }
+}
+
+// TMA-STAGED form of the tile kernel (d = 128, one segment): the neighbour rows of a tile do not travel through registers -- each
+// gathered row X[col[e], :] (512 B, contiguous) is ONE bulk async copy (cp.async.bulk.shared.global, SASS UBLKCP) into a per-warp ring in
+// shared memory, 8 rows per stage and kBulkStages stages per warp, each stage guarded by an mbarrier armed with the bytes it expects;
+// the warp then reads the staged rows conflict-free (lane = 16-byte chunk) and accumulates with the same row-boundary / epilogue logic
+// as the register kernel.  Per SM up to 12 warps x 3 stages x 4 KiB = 144 KiB of gathers are in flight without holding a register,
+// which is what a DRAM-latency-bound random gather wants.  Same tile descriptors, same sums in the same order (bit-identical results).
+constexpr bool kSpmmBulkAuto = false;   // flipped to true once the A/B on the large graph says so (tools/spmm_scale.py, LLMREC_SPMM_BULK=0/1)
+constexpr int kBulkStages = 4;
+constexpr int kBulkRows = 8;
+constexpr int kBulkWarps = 4;
+__device__ __forceinline__ void bulk_row_load(void* dst, const float* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(tc::smem_u32(dst)), "l"(src), "r"(bytes), "r"(tc::smem_u32(bar)) : "memory");
+}
+__global__ void __launch_bounds__(kBulkWarps * 32, 3) spmm_bulk_kernel(const SpmmParams p) {
+  extern __shared__ __align__(128) uint8_t bulk_smem[];
+  constexpr int ROWB = 512;                                        // d = 128 fp32
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* ring = bulk_smem + (size_t)warp * kBulkStages * kBulkRows * ROWB;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bulk_smem + (size_t)kBulkWarps * kBulkStages * kBulkRows * ROWB) + warp * kBulkStages;
+  if (lane == 0) {
+    for (int s = 0; s < kBulkStages; ++s) tc::mbar_init(&bars[s], 1);
+    tc::fence_barrier_init();
+  }
+  __syncwarp();
+  const int tile = blockIdx.x * kBulkWarps + warp;
+  if (tile >= p.n_tiles) return;
+  LaneChunks<1> lc;
+  setup_chunks<32, 1>(p, 0, lane, lc);
+  const int4 t = __ldg(p.tiles + 2 * tile);
+  const uint4 dl = __ldg(reinterpret_cast<const uint4*>(p.tiles + 2 * tile + 1));
+  const int row0 = t.x, nrows = t.y, e0 = t.z, e1 = t.w;
+  const bool piece = nrows == 0;
+  auto row_end_of = [&](int i) -> int {
+    const int b = i - 1;
+    const unsigned wsel = (b >> 2) == 0 ? dl.x : ((b >> 2) == 1 ? dl.y : ((b >> 2) == 2 ? dl.z : dl.w));
+    return e0 + (int)((wsel >> ((b & 3) * 8)) & 0xffu);
+  };
+  int cur = 0;
+  int row_end = piece ? e1 : row_end_of(1);
+  float4 acc[1] = {make_float4(0.f, 0.f, 0.f, 0.f)};
+  const int len = e1 - e0;
+  const int n_groups = (len + kBulkRows - 1) / kBulkRows;
+  const float* X = p.seg[0].X;
+  const int64_t ldx = p.seg[0].ldx;
+  // column / weight stream in 32-entry chunks: chunk c lives in (cidx[c & 1], w[c & 1]); the issue side runs < 32 entries ahead
+  int cidx0 = 0, cidx1 = 0;
+  float wv0 = 0.f, wv1 = 0.f;
+  auto load_chunk = [&](int c) {
+    const int e = e0 + c * 32 + lane;
+    int ci = 0; float w = 0.f;
+    if (e < e1) {
+      ci = __ldg(p.col + e);
+      w = p.vals ? __ldg(p.vals + e) : 1.0f;
+      if (p.cs) w *= __ldg(p.cs + ci);
+    }
+    if (c & 1) { cidx1 = ci; wv1 = w; } else { cidx0 = ci; wv0 = w; }
+  };
+  auto issue = [&](int g) {                                        // stage g % S <- rows of edges [8g, 8g + 8)
+    if ((g & 3) == 0) load_chunk(g >> 2);
+    const int s = g % kBulkStages;
+    const int k0 = g * kBulkRows;
+    const int nvalid = min(kBulkRows, len - k0);
+    const int cj = __shfl_sync(0xffffffffu, ((g >> 2) & 1) ? cidx1 : cidx0, (k0 + (lane & 7)) & 31);
+    if (lane == 0) tc::mbar_arrive_expect_tx(&bars[s], (uint32_t)nvalid * ROWB);
+    __syncwarp();
+    if (lane < nvalid) bulk_row_load(ring + ((size_t)s * kBulkRows + lane) * ROWB, X + (int64_t)cj * ldx, ROWB, &bars[s]);
+  };
+  const int pre = min(n_groups, kBulkStages - 1);
+  for (int g = 0; g < pre; ++g) issue(g);
+  for (int g = 0; g < n_groups; ++g) {
+    if (g + kBulkStages - 1 < n_groups) issue(g + kBulkStages - 1);
+    const int s = g % kBulkStages;
+    tc::mbar_wait(&bars[s], (uint32_t)((g / kBulkStages) & 1));
+    const int k0 = g * kBulkRows;
+    const int nvalid = min(kBulkRows, len - k0);
+    const float wmine = ((g >> 2) & 1) ? wv1 : wv0;
+#pragma unroll
+    for (int j = 0; j < kBulkRows; ++j) {
+      if (j < nvalid) {
+        const float wj = __shfl_sync(0xffffffffu, wmine, (k0 + j) & 31);
+        const int ge = e0 + k0 + j;
+        while (!piece && ge >= row_end) {
+          finish_row<1>(p, lc, acc, row0 + cur, 0xffffffffu);
+          ++cur;
+          row_end = row_end_of(cur + 1);
+        }
+        const float4 x = *reinterpret_cast<const float4*>(ring + ((size_t)s * kBulkRows + j) * ROWB + lane * 16);
+        fma4(acc[0], wj, x);
+      }
+    }
+    __syncwarp();                                                  // every lane has read stage s before it is refilled
+  }
+  if (piece) {
+    if (lane < p.total_f4) st4(p.scratch + ((int64_t)tile * p.total_f4 + lane) * 4, acc[0]);
+  } else {
+    for (; cur < nrows; ++cur) finish_row<1>(p, lc, acc, row0 + cur, 0xffffffffu);
   }
 }
 
@@ -431,6 +532,17 @@ extern "C" int llmrec_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, co
     p.src_mask = tiling->src_mask;
     LLMREC_CHECK_ARG(p.n_split == 0 || p.scratch != nullptr, "spmm: long-row pieces need the scratch buffer");
     int rc = 0;
+    static const int bulk_mode = getenv("LLMREC_SPMM_BULK") ? atoi(getenv("LLMREC_SPMM_BULK")) : -1;   // -1 auto, 0 off, 1 on
+    const bool bulk_ok = p.nseg == 1 && d == 128 && !p.src_mask && segs[s0].ldx == 128;
+    if (bulk_ok && (bulk_mode == 1 || (bulk_mode == -1 && kSpmmBulkAuto && (int64_t)n_cols * 512 > ((int64_t)192 << 20)))) {
+      const size_t smem = (size_t)kBulkWarps * kBulkStages * kBulkRows * 512 + kBulkWarps * kBulkStages * sizeof(uint64_t);
+      static bool attr = false;
+      if (!attr) { cudaFuncSetAttribute(spmm_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+      spmm_bulk_kernel<<<(p.n_tiles + kBulkWarps - 1) / kBulkWarps, kBulkWarps * 32, smem, st>>>(p);
+      LLMREC_CHECK_LAUNCH("spmm_bulk");
+      if (p.n_split > 0) { spmm_finish_kernel<1><<<dim3((p.n_split + 7) / 8, 1), 256, 0, st>>>(p); LLMREC_CHECK_LAUNCH("spmm_finish"); }
+      continue;
+    }
     if (p.total_f4 <= 8) rc = launch_spmm<8, 1, 4>(p, st);
     else if (p.total_f4 <= 16) rc = launch_spmm<16, 1, 4>(p, st);
     else {  // 32 lanes x one 16-byte chunk; wider concatenations run as 32-chunk column windows over blockIdx.y

@@ -112,6 +112,7 @@ class HotPath:
         self.n_heads = (3 + len(self.keys)) if self.has_feats else 1
         self.head_out = torch.zeros(self.n_heads * 4, dtype=torch.float32, device=dev)
         self._bpr_work, self._cap, self._graph = None, 0, None
+        self.pre_step = None              # optional launches replayed in front of every staged step (device-side batch sampler)
         self.opt = None
         self.timer = None
 
@@ -349,6 +350,8 @@ class HotPath:
                 # one eager step at full capacity sizes every lazily allocated scratch buffer; its parameter update is undone
                 snap = self._snapshot_state()
                 self._gidx[3, :2].copy_(self._meta_table[cap])
+                if self.pre_step is not None:
+                    self.pre_step()
                 self.train_step(u, p, n, meta)
                 self._restore_state(snap)
                 self._gidx.copy_(held)
@@ -356,6 +359,8 @@ class HotPath:
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
+                if self.pre_step is not None:
+                    self.pre_step()
                 self.train_step(u, p, n, meta)
             self._graph = g
         self._graph.replay()

@@ -135,7 +135,18 @@ class Trainer(object):
                                                aug_pos, aug_neg, aug_limit=self.n_items)
             self._batch_np = np.empty((3, 2 * data_generator.batch_size + 8), dtype=np.int32)
         self.use_graph = bool(getattr(args, "cuda_graph", 1))
-        self._epoch_stats = torch.zeros(3, dtype=torch.float32, device=self.device)
+        self._epoch_stats = torch.zeros(4, dtype=torch.float32, device=self.device)          # total, mf, emb, interactions (device-side sampler)
+        # --device_sampler 1: batches are drawn ON the GPU into the engine's index buffer, in front of every step
+        self.device_sampler = None
+        if getattr(args, "device_sampler", 0) and not self.masked_mode:
+            from .device_sampler import DeviceSampler
+            from .host_native import BatchSampler
+            rowptr, col = data_generator.csr("train", sorted_rows=True)
+            aug_pos, aug_neg = BatchSampler.aug_tables(self.augmented_sample_dict, data_generator.n_users)
+            self.device_sampler = DeviceSampler(data_generator.exist_users, rowptr, col, data_generator.n_items, data_generator.batch_size,
+                                                aug_pos, aug_neg, self.n_items, args.aug_sample_rate, self.device, seed=args.seed)
+            gi = self.hot.index_buffer(self.hot.batch_capacity())
+            self.hot.pre_step = lambda: self.device_sampler.fill(self.hot._gidx, self.hot._meta_table)
 
     # ---- reference helper API (same names / returns) ----------------------------------------------
     def csr_norm(self, csr_mat, mean_flag=False):
@@ -341,7 +352,20 @@ class Trainer(object):
         return self._step(*self.upload_batch(users, pos_items, neg_items))
 
     def train_next_batch(self):
-        """One iteration of the training loop (main.py:213-278): draw the next batch, run the step.  -> (loss tensor, B')."""
+        """One iteration of the training loop (main.py:213-278): draw the next batch, run the step.  -> (loss tensor, B').
+        With the device-side sampler B' is only known on the device (-1 here; Trainer.train reads the epoch total once)."""
+        if self.device_sampler is not None:
+            hp = self.hot
+            if self.use_graph:
+                loss = hp.replay_staged()
+            else:
+                hp.pre_step()
+                gi = hp._gidx
+                loss = hp.train_step(gi[0], gi[1], gi[2], gi[3])
+            self._epoch_stats[0:1] += loss
+            self._epoch_stats[1:3] += hp.head_out[0:2]
+            self._epoch_stats[3:4] += hp._gidx[3, 0:1].float()
+            return loss, -1
         u, p, n = self.stage_batch()
         return self._step(u, p, n), int(u.numel())
 
@@ -358,8 +382,9 @@ class Trainer(object):
             self.n_interactions = 0
             self.model_mm.train()
             for _ in range(n_batch):
-                self.n_interactions += self.train_next_batch()[1]
-            loss, mf_loss, emb_loss = (float(x) for x in self._epoch_stats.tolist())      # the one sync per epoch
+                self.n_interactions += max(self.train_next_batch()[1], 0)
+            loss, mf_loss, emb_loss, n_dev = (float(x) for x in self._epoch_stats.tolist())      # the one sync per epoch
+            self.n_interactions += int(n_dev)
             reg_loss, contrastive_loss = 0.0, 0.0
             if math.isnan(loss):
                 self.logger.logging("ERROR: loss is nan.")

@@ -512,12 +512,12 @@ def scaled_colsum(terms, out, accumulate=False):
 def feat_reg_gram(W, b, G, h, n2, c, dW, db, loss):
     """feat_reg over all rows through the Gram matrix G[k x k] of a propagated table (include/llmrec_b200.h)."""
     d, k = W.shape
-    key = ("gram", W.device.index, d)
+    key = ("gram", W.device.index, d, k)
     sc_ = _scratch.get(key)
     if sc_ is None:
-        sc_ = _scratch[key] = torch.zeros(d + 4, dtype=torch.float32, device=W.device)
+        sc_ = _scratch[key] = torch.zeros(int(N.lib().llmrec_feat_reg_gram_scratch(d, k)), dtype=torch.float32, device=W.device)
     N.check(N.lib().llmrec_feat_reg_gram_f32(_p(W), _p(b), _p(G), _p(h), float(n2), d, k, float(c), _p(dW), _p(db), _p(loss), _p(sc_), _stream()), "feat_reg_gram")
-    _count()
+    _count(2)
 
 
 def fill(t, v):

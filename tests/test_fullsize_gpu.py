@@ -1,6 +1,8 @@
 """-m gpu: size-independent properties of the DEFAULT kernels at the full sizes of BASELINE.json's netflix / movielens
 configurations (linearity, adjoint identity, idempotence, sortedness, exclusion) -- parity at shapes where every persistent
 kernel runs many tiles per CTA, which the tiny golden dataset cannot exercise."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -96,3 +98,35 @@ def test_fullsize_scoring_topk_properties():
     assert bool((S.max(dim=1).values <= picked[:, -1] + 1e-5).all())                                 # nothing outside beats the K-th
 
 
+
+
+def test_tma_staged_spmm_is_bit_identical_to_the_register_kernel():
+    """LLMREC_SPMM_BULK=1 routes d = 128 single-operand products through spmm_bulk_kernel (neighbour rows staged in shared memory by
+    cp.async.bulk + mbarriers): same tile plan, same summation order -> bit-identical output; softmax epilogue, addend, long rows."""
+    import subprocess
+    import sys
+    code = r"""
+import os, sys, numpy as np, torch
+sys.path.insert(0, %r)
+from tests.test_fullsize_gpu import _full_graph
+res = {}
+g, R, d = _full_graph("movielens")
+nu, ni = R.shape
+gen = torch.Generator().manual_seed(4)
+X, Z = torch.randn(ni, d, generator=gen).cuda(), torch.randn(nu, d, generator=gen).cuda()
+Xu = torch.randn(nu, d, generator=gen).cuda()
+out = []
+for sm, z in ((False, None), (True, None), (False, Z)):
+    Y = torch.empty(nu, d, device="cuda"); g.ui.apply([(X, Y, z, sm)]); out.append(Y.cpu())
+Yi = torch.empty(ni, d, device="cuda"); g.iu.apply([(Xu, Yi, None, False)]); out.append(Yi.cpu())       # item rows: long rows -> pieces + finish pass
+torch.save(out, sys.argv[1])
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    import tempfile
+    outs = []
+    for flag in ("0", "1"):
+        with tempfile.NamedTemporaryFile(suffix=".pt") as f:
+            r = subprocess.run([sys.executable, "-c", code, f.name], env=dict(os.environ, LLMREC_SPMM_BULK=flag), capture_output=True, text=True, timeout=600)
+            assert r.returncode == 0, r.stderr[-2000:]
+            outs.append(torch.load(f.name))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)

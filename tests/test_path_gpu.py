@@ -320,3 +320,40 @@ def test_mask_dropout_restoration_branch_matches_oracle(tiny_root):
         np.testing.assert_allclose(sd[k].cpu().numpy(), otr.params[k].detach().numpy(), rtol=3e-4, atol=3e-6, err_msg=k)
     res = tr.test(list(gen.test_set.keys()), is_val=False)          # eval keeps masking (Models.py:131-142 is unconditional)
     assert np.isfinite(res["recall"]).all()
+
+
+def test_device_sampler_batches_are_valid_and_reproducible(tiny_root):
+    """--device_sampler 1: structural validity of the batches the GPU draws (what Data.sample() + main.py:216-224
+    guarantee), reproducibility per seed, rough uniformity, and graph replay == eager launches on the same seed."""
+    tr, gen, M = _trainer(tiny_root, ["--device_sampler", "1", "--cuda_graph", "0"])
+    assert tr.device_sampler is not None
+    hp, ds = tr.hot, tr.device_sampler
+    B = gen.batch_size
+    aug = tr.augmented_sample_dict
+    seen, counts = [], np.zeros(gen.n_users)
+    for step in range(40):
+        hp.pre_step()
+        gi = hp._gidx.cpu().numpy()
+        Bp, n_keep = int(gi[3, 0]), int(gi[3, 1])
+        assert B <= Bp <= B + int(B * 0.1) and n_keep == int((1 - 0.71) * Bp)
+        u, p, n = gi[0, :Bp], gi[1, :Bp], gi[2, :Bp]
+        assert len(set(u[:B].tolist())) == B and set(u[:B].tolist()) <= set(gen.exist_users)                 # a subset, no repeats
+        for b in range(B):
+            items = gen.train_items[int(u[b])]
+            assert int(p[b]) in items and int(n[b]) not in items and 0 <= int(n[b]) < gen.n_items
+        for b in range(B, Bp):                                                                              # augmented edges: batch users, table values, valid ids
+            uu = int(u[b])
+            assert uu in set(u[:B].tolist()) and (int(p[b]), int(n[b])) == (aug[uu][0], aug[uu][1]) and max(aug[uu][0], aug[uu][1]) < gen.n_items
+        assert len(set(u[B:Bp].tolist())) == Bp - B
+        seen.append(u[:B].copy()); counts[u[:B]] += 1
+    assert not np.array_equal(np.sort(seen[0]), np.sort(seen[1]))
+    expect = 40 * B / len(gen.exist_users)
+    assert counts[gen.exist_users].min() >= 1 and abs(counts[gen.exist_users].mean() - expect) < 1e-6 and counts.max() < 3 * expect + 10
+    # same seed -> same batches; graph replay == eager
+    a, _, _ = _trainer(tiny_root, ["--device_sampler", "1", "--cuda_graph", "0"])
+    b, _, _ = _trainer(tiny_root, ["--device_sampler", "1", "--cuda_graph", "1"])
+    la = [float(a.train_next_batch()[0]) for _ in range(5)]
+    lb = [float(b.train_next_batch()[0]) for _ in range(5)]
+    assert all(abs(x - y) <= 2e-5 * max(1.0, abs(x)) for x, y in zip(la, lb)), (la, lb)
+    assert np.isfinite(la).all()
+    assert int(a._epoch_stats[3]) == int(b._epoch_stats[3]) >= 5 * B
