@@ -91,7 +91,8 @@ int llmrec_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, const float* 
  * neighbourhood -- dist.py "demand" mode).  Persistent grid, no host synchronisation. */
 int llmrec_spmm_rows_f32(const int32_t* rowptr, const int32_t* col, const float* vals, const float* row_scale, const float* col_scale,
                          int32_t d, const llmrec_spmm_seg* seg_host, const int32_t* rows, const int32_t* n_rows_dev, int32_t max_rows,
-                         const uint32_t* src_mask, llmrec_stream_t stream);
+                         const uint32_t* src_mask, int32_t cta_per_row /* 1: one CTA per listed row -- short lists of possibly very long rows */,
+                         llmrec_stream_t stream);
 int llmrec_row_softmax_bwd_rows_f32(const float* S, int64_t lds, const float* dS, int64_t ldds, float* dX, int64_t lddx,
                                     const int32_t* rows, const int32_t* n_rows_dev, int32_t max_rows, int32_t d, llmrec_stream_t stream);
 /* Device-side row sets: mask |= {col[e] : e in rows list[.] of the CSR}, mask |= {ids}, and mask -> (unordered) id list with *count += #bits. */

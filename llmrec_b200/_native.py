@@ -66,7 +66,7 @@ SIGNATURES = {
     "llmrec_spmm_csr_f32": (C.c_int, [c_i32p, c_i32p, c_f32p, c_f32p, c_f32p, C.c_int32, C.c_int32, C.c_int32,
                                       C.POINTER(SpmmSeg), C.c_int32, C.POINTER(SpmmTiling), c_stream]),
     "llmrec_spmm_plan_tiles": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "llmrec_spmm_rows_f32": (C.c_int, [c_i32p, c_i32p, c_f32p, c_f32p, c_f32p, C.c_int32, C.POINTER(SpmmSeg), c_i32p, c_i32p, C.c_int32, C.c_void_p, c_stream]),
+    "llmrec_spmm_rows_f32": (C.c_int, [c_i32p, c_i32p, c_f32p, c_f32p, c_f32p, C.c_int32, C.POINTER(SpmmSeg), c_i32p, c_i32p, C.c_int32, C.c_void_p, C.c_int32, c_stream]),
     "llmrec_row_softmax_bwd_rows_f32": (C.c_int, [c_f32p, C.c_int64, c_f32p, C.c_int64, c_f32p, C.c_int64, c_i32p, c_i32p, C.c_int32, C.c_int32, c_stream]),
     "llmrec_mark_neighbors": (C.c_int, [c_i32p, c_i32p, c_i32p, C.c_int32, C.c_void_p, c_stream]),
     "llmrec_mark_ids": (C.c_int, [c_i32p, C.c_int32, C.c_void_p, c_stream]),

@@ -74,7 +74,49 @@ __global__ void __launch_bounds__(256) scaled_colsum_kernel(const ColsumParams p
   if (threadIdx.x == 0) p.ticket[blockIdx.x] = 0u;
 }
 
-// Second half of feat_reg_gram: WG = W G was formed by the exact-fp32 SIMT GEMM (proj_fwd_simt: Y = X W'^T with X = W, W' = G = G^T).
+// First half of feat_reg_gram: WG = W G for W[d x k], G[k x k] symmetric, as split-K partial tiles (75 MFLOP at k = 768: a 12-CTA GEMM takes
+// 100 us, 96 CTAs take ~5).  grid (k/64 column tiles, kGramSplit K-chunks, d/64 row tiles); part[ks][i][j] holds the chunk's partial sum;
+// the finish kernel adds the chunks in a fixed order (deterministic).
+constexpr int kGramSplit = 8;
+__global__ void __launch_bounds__(256) gram_wg_kernel(const float* __restrict__ W, const float* __restrict__ G, int d, int k, float* __restrict__ part) {
+  __shared__ float Ws[16][64 + 4];   // [kk][row i]
+  __shared__ float Gs[16][64 + 4];   // [kk][col j]
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int j0 = blockIdx.x * 64, i0 = blockIdx.z * 64;
+  const int chunk = (k + kGramSplit - 1) / kGramSplit;
+  const int l_beg = blockIdx.y * chunk, l_end = min(k, l_beg + chunk);
+  float acc[4][4] = {};
+  for (int l0 = l_beg; l0 < l_end; l0 += 16) {
+    for (int t = threadIdx.x; t < 64 * 16; t += 256) {
+      const int r = t >> 4, kk = t & 15;                 // W tile: consecutive threads walk k (contiguous in W)
+      Ws[kk][r] = (i0 + r < d && l0 + kk < l_end) ? W[(size_t)(i0 + r) * k + l0 + kk] : 0.f;
+      const int kk2 = t >> 6, c = t & 63;                // G tile: consecutive threads walk columns (contiguous in G)
+      Gs[kk2][c] = (j0 + c < k && l0 + kk2 < l_end) ? __ldg(G + (size_t)(l0 + kk2) * k + j0 + c) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { a[q] = Ws[kk][ty * 4 + q]; b[q] = Gs[kk][tx * 4 + q]; }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[q][r] = fmaf(a[q], b[r], acc[q][r]);
+    }
+    __syncthreads();
+  }
+  float* out = part + (size_t)blockIdx.y * d * k;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int i = i0 + ty * 4 + q;
+    if (i >= d) continue;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) { const int j = j0 + tx * 4 + r; if (j < k) out[(size_t)i * k + j] = acc[q][r]; }
+  }
+}
+
+// Second half of feat_reg_gram: WG[i,:] = sum over the kGramSplit partial tiles of gram_wg_kernel (fixed order).
 // One CTA per row i of W[d x k]:  dW[i,:] += c (WG[i,:] + b_i h^T);  db_i += c (W[i,:].h + n2 b_i);
 // loss += c/2 (WG[i,:].W[i,:] + 2 b_i W[i,:].h + n2 b_i^2) summed over i in a fixed order by the last CTA.
 __global__ void __launch_bounds__(256) feat_reg_finish_kernel(const float* __restrict__ W, const float* __restrict__ b, const float* __restrict__ WG,
@@ -86,7 +128,10 @@ __global__ void __launch_bounds__(256) feat_reg_finish_kernel(const float* __res
   const float bi = b ? b[i] : 0.f;
   float quad = 0.f, wh = 0.f;
   for (int j = threadIdx.x; j < k; j += blockDim.x) {
-    const float w = W[(size_t)i * k + j], a = WG[(size_t)i * k + j];
+    const float w = W[(size_t)i * k + j];
+    float a = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < kGramSplit; ++ks) a += WG[((size_t)ks * d + i) * k + j];
     const float hj = h ? __ldg(h + j) : 0.f;
     quad = fmaf(a, w, quad);
     wh = fmaf(w, hj, wh);
@@ -118,7 +163,6 @@ __global__ void __launch_bounds__(256) feat_reg_finish_kernel(const float* __res
     *ticket = 0u;
   }
 }
-int proj_fwd_simt(const float*, int64_t, const float*, const float*, float*, int64_t, int64_t, int, int, cudaStream_t);
 }  // namespace llmrec
 
 using namespace llmrec;
@@ -155,16 +199,16 @@ extern "C" int llmrec_scaled_colsum_f32(const llmrec_colsum_term* terms, int32_t
   return 0;
 }
 
-extern "C" int64_t llmrec_feat_reg_gram_scratch(int32_t d, int32_t k) { return (int64_t)d * k + d + 4; }
+extern "C" int64_t llmrec_feat_reg_gram_scratch(int32_t d, int32_t k) { return (int64_t)kGramSplit * d * k + d + 4; }
 
 extern "C" int llmrec_feat_reg_gram_f32(const float* W, const float* bias, const float* G, const float* h, float n2, int32_t d, int32_t k, float c,
                                         float* dW, float* db, float* loss_accum, float* scratch, llmrec_stream_t stream) {
   LLMREC_REQUIRE_DEVICE();
   LLMREC_CHECK_ARG(d >= 1 && k >= 1 && scratch, "feat_reg_gram: d=%d k=%d out of range", d, k);
   cudaStream_t st = as_stream(stream);
-  float* WG = scratch + d + 4;                                    // [d x k] after the partial/ticket block
-  int rc = proj_fwd_simt(W, k, G, nullptr, WG, k, d, k, k, st);   // WG = W G^T = W G (G symmetric): exact fp32, 64 x 64 tiles
-  if (rc) return rc;
+  float* WG = scratch + d + 4;                                    // [kGramSplit][d x k] partial tiles after the partial/ticket block
+  gram_wg_kernel<<<dim3((k + 63) / 64, kGramSplit, (d + 63) / 64), 256, 0, st>>>(W, G, d, k, WG);
+  LLMREC_CHECK_LAUNCH("gram_wg");
   feat_reg_finish_kernel<<<d, 256, 0, st>>>(W, bias, WG, h, n2, d, k, c, dW, db, loss_accum, scratch, reinterpret_cast<unsigned*>(scratch + d));
   LLMREC_CHECK_LAUNCH("feat_reg_finish");
   return 0;

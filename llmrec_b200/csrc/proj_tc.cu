@@ -544,14 +544,16 @@ int proj_fwd_tc_group(const llmrec_proj_fwd_problem* pr, int n_prob, int d, int 
   P.total_tiles = tiles;
   static const bool krot = getenv("LLMREC_PROJ_KROT") != nullptr;
   P.krot = krot ? 1 : 0;
-  static const bool skipw = getenv("LLMREC_PROJ_SKIPW") != nullptr;
-  P.skipw = skipw ? 1 : 0;
+  static const int skipw = getenv("LLMREC_PROJ_SKIPW") ? atoi(getenv("LLMREC_PROJ_SKIPW")) : 0;   // TIMING experiments (wrong results): 1 no W loads, 2 no MMAs, 4 no transform
+  P.skipw = skipw;
   uint32_t smem;
   P.stages = stages_for(d, split, &smem);
   P.tmem_cols = (int)pow2_cols(2 * d);
   int grid = tiles < 148 ? tiles : 148;
   if (grid <= 0) return 0;
   static const bool force_v1 = getenv("LLMREC_PROJ_V1") != nullptr;
+  static const int fwd_v = getenv("LLMREC_PROJ_FWD_V") ? atoi(getenv("LLMREC_PROJ_FWD_V")) : 3;
+  if (split && d <= 128 && !force_v1 && fwd_v == 3 && !wbox) return proj_fwd_ts3_launch(P, grid, st);   // decoupled A / W / TMEM rings (proj_tc2.cu)
   if (split && d <= 128 && !force_v1) return proj_fwd_ts_launch(P, grid, st);   // A operand from tensor memory (proj_tc2.cu)
   if (split) {
     cudaFuncSetAttribute(proj_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -626,8 +628,11 @@ int proj_wgrad_tc_group(const llmrec_proj_wgrad_problem* pr, int n_prob, int d, 
   int grid = items < 148 ? items : 148;
   if (grid <= 0) return 0;
   static const bool force_v1 = getenv("LLMREC_PROJ_V1") != nullptr;
+  static const int wg_v = getenv("LLMREC_PROJ_WG_V") ? atoi(getenv("LLMREC_PROJ_WG_V")) : 3;
+  bool any3d = false;
+  for (int p = 0; p < n_prob; ++p) any3d = any3d || P.prob[p].x3d || P.prob[p].g3d;
   if (split && d <= 128 && !force_v1) {
-    int rc = proj_wgrad_ts_launch(P, grid, st);
+    int rc = (wg_v == 3 && !any3d) ? proj_wgrad_ts3_launch(P, grid, st) : proj_wgrad_ts_launch(P, grid, st);   // decoupled X / dY / TMEM rings vs v2
     if (rc) return rc;
   } else if (split) {
     cudaFuncSetAttribute(proj_wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

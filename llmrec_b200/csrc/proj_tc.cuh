@@ -16,6 +16,7 @@ struct FwdParams {
   CUtensorMap tmW[kMaxProb];  // [2d x k] (hi rows then lo rows) when SPLIT, [d x k] otherwise
   FwdProblem prob[kMaxProb];
   int n_prob, total_tiles, d, stages, tmem_cols;
+  int nw, nt; // v3 forward (proj_fwd_ts3_kernel): slots of the W ring and of the TMEM A ring (`stages` = slots of the smem A ring)
   int wbox;   // experiment (LLMREC_PROJ_WBOX): W_hi and W_lo of a k-block arrive as ONE [2d x 32] TMA box (they are adjacent rows of the split matrix and adjacent in the stage)
   int skipw;  // TIMING experiment only (LLMREC_PROJ_SKIPW, results are wrong): the W tiles are not fetched, isolating the L2->SM cost of re-reading W per k-block
   int krot;   // experiment (LLMREC_PROJ_KROT): CTA b starts its k loop at block b mod kblocks, so concurrent CTAs read different columns
@@ -29,11 +30,14 @@ struct WgParams {
   CUtensorMap tmG[kMaxProb];
   WgProblem prob[kMaxProb];
   int n_prob, total_items, d, stages, tmem_cols;
+  int ng, nt; // v3 wgrad (proj_wgrad_ts3_kernel): slots of the dY ring and of the TMEM A ring (`stages` = slots of the smem X ring)
   float* partial;  // [total_items][128][d]
 };
 
 
 int proj_fwd_ts_launch(const FwdParams& P, int grid, cudaStream_t st);
+int proj_fwd_ts3_launch(const FwdParams& P, int grid, cudaStream_t st);
 int proj_wgrad_ts_launch(const WgParams& P, int grid, cudaStream_t st);
+int proj_wgrad_ts3_launch(const WgParams& P, int grid, cudaStream_t st);
 
 }  // namespace llmrec

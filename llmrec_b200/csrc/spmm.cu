@@ -340,6 +340,70 @@ __global__ void __launch_bounds__(256) spmm_rows_kernel(const SpmmParams p) {
   }
 }
 
+// Row-list form for SHORT lists of possibly very LONG rows (the 2B' batch items of a step: a hub item has 1e5 neighbours): one CTA of 8
+// warps per listed row, warp w takes the row's 32-edge chunks w, w+8, ..; the 8 partial rows are added in warp order through shared
+// memory (deterministic), then the same epilogue.  d = 128 (lane = 16-byte chunk), one segment.
+__global__ void __launch_bounds__(256) spmm_rows_cta_kernel(const SpmmParams p) {
+  __shared__ float4 part[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int n = __ldg(p.n_rows_dev);
+  n = n < p.max_rows ? n : p.max_rows;
+  const llmrec_spmm_seg sg = p.seg[0];
+  const int f4 = p.d >> 2;                                   // 8, 16 or 32 chunks per row; lanes >= f4 idle in the gathers
+  for (int idx = blockIdx.x; idx < n; idx += gridDim.x) {
+    const int row = __ldg(p.rows + idx);
+    if (row < 0) continue;
+    const int e0 = __ldg(p.rowptr + row), e1 = __ldg(p.rowptr + row + 1);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k0 = e0 + w * 32; k0 < e1; k0 += 8 * 32) {
+      const int e = k0 + lane;
+      int cidx = 0; float wt = 0.f;
+      if (e < e1) {
+        cidx = __ldg(p.col + e);
+        wt = p.vals ? __ldg(p.vals + e) : 1.0f;
+        if (p.cs) wt *= __ldg(p.cs + cidx);
+        if (p.src_mask && !src_active(p.src_mask, cidx)) wt = 0.f;
+      }
+      const int cnt = min(32, e1 - k0);
+      for (int j0 = 0; j0 < cnt; j0 += 4) {
+        float4 x[4]; float wj[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int cj = __shfl_sync(0xffffffffu, cidx, (j0 + u) & 31);
+          wj[u] = __shfl_sync(0xffffffffu, wt, (j0 + u) & 31);
+          const bool live = j0 + u < cnt && lane < f4 && (!p.src_mask || wj[u] != 0.f);
+          x[u] = live ? ldg4(sg.X + (int64_t)cj * sg.ldx + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) if (j0 + u < cnt) fma4(acc, wj[u], x[u]);
+      }
+    }
+    part[w][lane] = acc;
+    __syncthreads();
+    if (w == 0) {
+      float4 a = part[0][lane];
+#pragma unroll
+      for (int q = 1; q < 8; ++q) { const float4 b = part[q][lane]; a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+      const float sc = p.rs ? __ldg(p.rs + row) : 1.0f;
+      a.x *= sc; a.y *= sc; a.z *= sc; a.w *= sc;
+      if (sg.flags & LLMREC_SPMM_SOFTMAX) {
+        float m = lane < f4 ? fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)) : -INFINITY;
+        m = warp_max(m);
+        float4 ev = make_float4(expf(a.x - m), expf(a.y - m), expf(a.z - m), expf(a.w - m));
+        float t = lane < f4 ? (ev.x + ev.y) + (ev.z + ev.w) : 0.f;
+        t = warp_sum(t);
+        const float inv = 1.0f / t;
+        a = make_float4(ev.x * inv, ev.y * inv, ev.z * inv, ev.w * inv);
+      }
+      if (lane < f4) {
+        if (sg.Z) { const float4 z = *reinterpret_cast<const float4*>(sg.Z + (int64_t)row * sg.ldz + lane * 4); a.x += z.x; a.y += z.y; a.z += z.z; a.w += z.w; }
+        st4(sg.Y + (int64_t)row * sg.ldy + lane * 4, a);
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // second pass for long rows: ordered sum of the piece partials, then the fused epilogue (one warp per row and window)
 template <int CH>
 __global__ void __launch_bounds__(256) spmm_finish_kernel(const SpmmParams p) {
@@ -562,7 +626,7 @@ extern "C" int llmrec_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, co
 
 extern "C" int llmrec_spmm_rows_f32(const int32_t* rowptr, const int32_t* col, const float* vals, const float* row_scale, const float* col_scale,
                                     int32_t d, const llmrec_spmm_seg* seg, const int32_t* rows, const int32_t* n_rows_dev, int32_t max_rows,
-                                    const uint32_t* src_mask, llmrec_stream_t stream) {
+                                    const uint32_t* src_mask, int32_t cta_per_row, llmrec_stream_t stream) {
   LLMREC_REQUIRE_DEVICE();
   LLMREC_CHECK_ARG(seg && rows && n_rows_dev && max_rows >= 0, "spmm_rows: row list, its device-side length and a segment are required");
   LLMREC_CHECK_ARG((d == 32 || d == 64 || d == 128) && aligned16(seg->X) && aligned16(seg->Y) && seg->ldx % 4 == 0 && seg->ldy % 4 == 0 &&
@@ -575,6 +639,11 @@ extern "C" int llmrec_spmm_rows_f32(const int32_t* rowptr, const int32_t* col, c
   long long want = ((long long)max_rows + 8LL * rpw - 1) / (8LL * rpw);
   const int blocks = (int)(want < 148 * 8 ? want : 148 * 8);          // persistent: 8 CTAs of 8 warps per SM
   cudaStream_t st = as_stream(stream);
+  if (cta_per_row) {
+    spmm_rows_cta_kernel<<<max_rows < 148 * 8 ? max_rows : 148 * 8, 256, 0, st>>>(p);
+    LLMREC_CHECK_LAUNCH("spmm_rows_cta");
+    return 0;
+  }
   if (lpr == 32) spmm_rows_kernel<32, 4><<<blocks, 256, 0, st>>>(p);
   else if (lpr == 16) spmm_rows_kernel<16, 4><<<blocks, 256, 0, st>>>(p);
   else spmm_rows_kernel<8, 4><<<blocks, 256, 0, st>>>(p);

@@ -289,7 +289,7 @@ class ShardedHotPath:
             self._exchange("iu", self.Ul[l])
             ops.row_scale_softmax(self.part, g.si, self.Il[l], False)
         g.ui.apply_rows((self.Il[L - 1], self.Ul[L], None, True), rows, cnt)                  # U_L = softmax(ui . I_{L-1}) on needU
-        g.iu_raw.apply_rows((self.Ul[L], self.part, None, False), pn, self.cnt_pn)            # this rank's partial of R^T U_L on the batch items
+        g.iu_raw.apply_rows((self.Ul[L], self.part, None, False), pn, self.cnt_pn, cta_per_row=True)   # this rank's partial of R^T U_L on the batch items (hub items: 1e5 neighbours)
         ops.gather_rows(self.part, pn, self.Pc)
         self._allreduce(self.Pc)                                                              # [2B' x d] instead of [ni x d]
         ops.gather_rows(g.si.view(-1, 1), pn, self.sic)

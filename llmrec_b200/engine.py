@@ -113,6 +113,7 @@ class HotPath:
         self.head_out = torch.zeros(self.n_heads * 4, dtype=torch.float32, device=dev)
         self._bpr_work, self._cap, self._graph = None, 0, None
         self.pre_step = None              # optional launches replayed in front of every staged step (device-side batch sampler)
+        self.pre_step_undo = None         # undoes the side effect of ONE pre_step (the warm-up step before a capture must not consume a batch)
         self.opt = None
         self.timer = None
 
@@ -354,6 +355,8 @@ class HotPath:
                     self.pre_step()
                 self.train_step(u, p, n, meta)
                 self._restore_state(snap)
+                if self.pre_step is not None and self.pre_step_undo is not None:
+                    self.pre_step_undo()
                 self._gidx.copy_(held)
                 self._warm = True
             torch.cuda.synchronize()

@@ -147,6 +147,7 @@ class Trainer(object):
                                                 aug_pos, aug_neg, self.n_items, args.aug_sample_rate, self.device, seed=args.seed)
             gi = self.hot.index_buffer(self.hot.batch_capacity())
             self.hot.pre_step = lambda: self.device_sampler.fill(self.hot._gidx, self.hot._meta_table)
+            self.hot.pre_step_undo = lambda: self.device_sampler.state[1:2].sub_(1)
 
     # ---- reference helper API (same names / returns) ----------------------------------------------
     def csr_norm(self, csr_mat, mean_flag=False):

@@ -97,7 +97,7 @@ class CsrOperator:
             k.scratch = torch.empty(need, dtype=torch.float32, device=self.rowptr.device)
         return N.SpmmTiling(_p(k.tiles), _p(k.split_row), _p(k.split_first), _p(k.scratch), k.n_tiles, k.n_split, k.n_split_tiles, 0, None)
 
-    def apply_rows(self, seg, rows, count, max_rows=None, src_mask=None):
+    def apply_rows(self, seg, rows, count, max_rows=None, src_mask=None, cta_per_row=False):
         """Row-list form (llmrec_spmm_rows_f32): only rows[0 .. count[0]) are computed and written.  seg = (X, Y, Z|None, softmax);
         rows: int32 CUDA list, count: int32[1] CUDA (device-side length), src_mask: optional uint32/int32 bitmask over source rows."""
         X, Y, Z, sm = seg
@@ -108,7 +108,7 @@ class CsrOperator:
         sg = N.SpmmSeg(_p(X), _p(Y), _p(Z) if Z is not None else None, _ld(X), _ld(Y), _ld(Z) if Z is not None else 0, N.SPMM_SOFTMAX if sm else 0, 0)
         mx = int(rows.numel()) if max_rows is None else int(max_rows)
         N.check(N.lib().llmrec_spmm_rows_f32(_p(self.rowptr), _p(self.col), _p(self.vals), _p(self.rs), _p(self.cs), d, C.byref(sg),
-                                              _p(_i32(rows)), _p(count), mx, _p(src_mask), _stream()), "spmm_rows")
+                                              _p(_i32(rows)), _p(count), mx, _p(src_mask), 1 if cta_per_row else 0, _stream()), "spmm_rows")
         _count()
 
     def apply(self, segs, src_mask=None):

@@ -15,7 +15,7 @@ class CsrOperator:
         self.plan = plan if plan is not None else object()
         assert self.rowptr.numel() == self.n_rows + 1
 
-    def apply_rows(self, seg, rows, count, max_rows=None, src_mask=None):          # llmrec_spmm_rows_f32: listed rows only
+    def apply_rows(self, seg, rows, count, max_rows=None, src_mask=None, cta_per_row=False):          # llmrec_spmm_rows_f32: listed rows only
         X, Y, Z, sm = seg
         full = torch.empty_like(Y)
         self.apply([(X if src_mask is None else _masked_rows(X, src_mask), full, Z, sm)])

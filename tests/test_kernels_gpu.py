@@ -453,6 +453,18 @@ def test_spmm_row_list_and_source_mask_match_the_full_product(d):
         listed = torch.zeros(nu, dtype=torch.bool, device=cuda); listed[rs.list[:n].long()] = True
         torch.testing.assert_close(out[listed], full[listed], rtol=1e-5, atol=1e-6)
         assert bool((out[~listed] == 777.0).all())
+    # one CTA per listed row (short list, long rows: the hub items of a batch), softmax + addend fused, duplicates in the list
+    Xu = torch.randn(nu, d, generator=gen).to(cuda); Zi = torch.randn(ni, d, generator=gen).to(cuda)
+    hubs = torch.tensor([0, 1, 2, 0, 777, -1, 1499], dtype=torch.int32, device=cuda)            # items 0.. are the most popular ones
+    cnt = torch.tensor([hubs.numel()], dtype=torch.int32, device=cuda)
+    for sm in (False, True):
+        fi = torch.empty(ni, d, device=cuda); g.iu.apply([(Xu, fi, Zi, sm)])
+        oi = torch.full((ni, d), 555.0, device=cuda)
+        g.iu.apply_rows((Xu, oi, Zi, sm), hubs, cnt, cta_per_row=True)
+        sel = hubs[hubs >= 0].long()
+        torch.testing.assert_close(oi[sel], fi[sel], rtol=2e-5, atol=2e-6)
+        rest = torch.ones(ni, dtype=torch.bool, device=cuda); rest[sel] = False
+        assert bool((oi[rest] == 555.0).all())
     # source mask: rows of the operand outside the set hold NaN and must never be fetched
     Y = torch.randn(nu, d, generator=gen).to(cuda)
     keep = torch.zeros(nu, dtype=torch.bool, device=cuda); keep[rs.list[:n].long()] = True
