@@ -111,7 +111,7 @@ def make_trainer(workload, a, extra=()):
     ds, nu, ni, ne, dims, embed, wsize = WORKLOADS[workload]
     root = ensure_dataset(workload)
     args = set_args(parse_args(["--data_path", root, "--dataset", ds, "--debug", "--epoch", "1", "--embed_size", str(embed),
-                                "--weight_size", wsize, "--proj_mode", a.proj_mode, "--feat_layout", a.feat_layout, "--host_sampler", a.host_sampler,
+                                "--weight_size", wsize, "--proj_mode", a.proj_mode, "--host_sampler", a.host_sampler,
                                 "--cuda_graph", str(a.graph)] + list(extra)))
     torch.cuda.set_device(0)
     M.set_seed(args.seed)
@@ -390,7 +390,7 @@ def run_ours(a):
            "data": "synthetic", "impl": "ours",
            "config": {"workload": workload_string(a.workload), "train_edges": main["train_edges"],
                       "interactions_counted": "sum(len(users)) incl. augmented edges", "l2": "inputs larger than L2 (704 MB of features per step)",
-                      "proj_mode": a.proj_mode, "feat_layout": a.feat_layout, "host_sampler": a.host_sampler, "cuda_graph": bool(a.graph),
+                      "proj_mode": a.proj_mode, "host_sampler": a.host_sampler, "cuda_graph": bool(a.graph),
                       "timing": f"median of {main['blocks']} blocks of {K} steps (>= {a.min_seconds} s of device time)",
                       "ms_per_step_min": main["ms_per_step_min"], "ms_per_step_max": main["ms_per_step_max"]},
            "e2e": main["e2e"], "gpu_launches": main["gpu_launches"], "clocks": clk, "roofline": main["roofline"], "eval": main["eval"]}
@@ -477,7 +477,6 @@ def main():
     ap.add_argument("--eval-users", dest="eval_users", type=int, default=102400, help="users ranked in the synthetic eval leg")
     ap.add_argument("--syn-scale", dest="syn_scale", type=float, default=1.0, help="size factor of the 10M x 1M x 200M synthetic graph")
     ap.add_argument("--proj_mode", default="3xtf32")
-    ap.add_argument("--feat_layout", default="rows", choices=["rows", "panels"])
     ap.add_argument("--host_sampler", default="native")
     ap.add_argument("--no-cpu", dest="no_cpu", action="store_true")
     ap.add_argument("--gpu-baseline", dest="gpu_baseline", type=int, default=1)

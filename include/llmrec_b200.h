@@ -131,28 +131,14 @@ int64_t llmrec_proj_wgrad_scratch(int64_t n, int32_t k, int32_t d, int32_t mode)
 typedef struct {
   const float* X; const float* W; const float* bias; float* Y; float* wsplit;
   int64_t ldx, ldy, n;
-  int32_t k, x_layout;        /* LLMREC_X_ROWS | LLMREC_X_PANELS */
+  int32_t k, _reserved;       /* 0 */
 } llmrec_proj_fwd_problem;
 typedef struct {
   const float* X; const float* dY; float* dW; float* db;
   int64_t ldx, lddy, n;
-  int32_t k, accumulate;      /* LLMREC_WGRAD_ACCUMULATE | LLMREC_WGRAD_X_PANELS */
+  int32_t k, accumulate;      /* LLMREC_WGRAD_ACCUMULATE */
 } llmrec_proj_wgrad_problem;
-/* Layout of the constant feature table X[n x k] a problem reads (the reference keeps these as plain row-major buffers,
- * Models.py:43-48; they never change during training, so their HBM layout is ours to choose):
- *   LLMREC_X_ROWS    row-major, leading dimension ldx;
- *   LLMREC_X_PANELS  the output of llmrec_panelize_f32: k/32 column panels, panel p = X[:, 32p : 32p+32] stored as a
- *                    contiguous [n_pad x 32] block (n_pad = LLMREC_PANEL_ROWS(n) = n rounded up to 128, padding rows
- *                    zero), so every [rows x 32] tile the tensor-core kernels fetch is ONE contiguous run of DRAM
- *                    instead of 128-byte pieces at a row pitch of 4k bytes.  k % 32 == 0; ldx is ignored; tcgen05 modes
- *                    only (mode 2 rejects it). */
-#define LLMREC_X_ROWS 0
-#define LLMREC_X_PANELS 1
 #define LLMREC_WGRAD_ACCUMULATE 1
-#define LLMREC_WGRAD_X_PANELS 2
-/* Xp[(p*n_pad + r)*32 + c] = r < n ? X[r*ldx + 32p + c] : 0   (one-time re-layout; Xp holds n_pad*k floats) */
-#define LLMREC_PANEL_ROWS(n) ((((int64_t)(n)) + 127) / 128 * 128)
-int llmrec_panelize_f32(const float* X, int64_t ldx, int64_t n, int32_t k, float* Xp, llmrec_stream_t stream);
 int llmrec_proj_fwd_group_f32(const llmrec_proj_fwd_problem* probs_host, int32_t n_prob, int32_t d, int32_t mode,
                               llmrec_stream_t stream);
 int llmrec_proj_wgrad_group_f32(const llmrec_proj_wgrad_problem* probs_host, int32_t n_prob, int32_t d, int32_t mode,

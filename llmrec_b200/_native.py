@@ -30,7 +30,7 @@ class SpmmTiling(C.Structure):
 
 class ProjFwdProblem(C.Structure):
     _fields_ = [("X", C.c_void_p), ("W", C.c_void_p), ("bias", C.c_void_p), ("Y", C.c_void_p), ("wsplit", C.c_void_p),
-                ("ldx", C.c_int64), ("ldy", C.c_int64), ("n", C.c_int64), ("k", C.c_int32), ("x_layout", C.c_int32)]
+                ("ldx", C.c_int64), ("ldy", C.c_int64), ("n", C.c_int64), ("k", C.c_int32), ("_reserved", C.c_int32)]
 
 
 class ProjWgradProblem(C.Structure):
@@ -119,7 +119,6 @@ SIGNATURES = {
     "llmrec_feat_reg_gram_f32": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_float, C.c_int32, C.c_int32, C.c_float, c_f32p, c_f32p, c_f32p, c_f32p, c_stream]),
     "llmrec_feat_reg_gram_scratch": (C.c_int64, [C.c_int32, C.c_int32]),
     "llmrec_fill_f32": (C.c_int, [c_f32p, C.c_int64, C.c_float, c_stream]),
-    "llmrec_panelize_f32": (C.c_int, [c_f32p, C.c_int64, C.c_int64, C.c_int32, c_f32p, c_stream]),
 }
 
 _lib = None

@@ -41,7 +41,6 @@ extern "C" int llmrec_proj_fwd_group_f32(const llmrec_proj_fwd_problem* pr, int3
       int rc = proj_fwd_tc_group(pr + p0, np, d, mode, st);
       if (rc) return rc;
     } else {
-      for (int p = p0; p < p0 + np; ++p) LLMREC_CHECK_ARG(pr[p].x_layout == LLMREC_X_ROWS, "proj_fwd_group: the panel layout needs the tcgen05 path (mode 0/1, supported shapes)");
       for (int p = p0; p < p0 + np; ++p) {
         if (pr[p].n <= 0) continue;
         int rc = proj_fwd_simt(pr[p].X, pr[p].ldx, pr[p].W, pr[p].bias, pr[p].Y, pr[p].ldy, pr[p].n, pr[p].k, d, st);
@@ -78,7 +77,6 @@ extern "C" int llmrec_proj_wgrad_group_f32(const llmrec_proj_wgrad_problem* pr, 
       if (rc) return rc;
     } else {
       for (int p = p0; p < p0 + np; ++p) {
-        LLMREC_CHECK_ARG(!(pr[p].accumulate & LLMREC_WGRAD_X_PANELS), "proj_wgrad_group: the panel layout needs the tcgen05 path (mode 0/1, supported shapes)");
         int rc = proj_wgrad_simt(pr[p].X, pr[p].ldx, pr[p].dY, pr[p].lddy, pr[p].dW, pr[p].db, pr[p].n, pr[p].k, d, pr[p].accumulate & LLMREC_WGRAD_ACCUMULATE, st);
         if (rc) return rc;
       }

@@ -143,12 +143,10 @@ __global__ void __launch_bounds__(384, 1) proj_fwd_tc_kernel(const __grid_consta
       for (int kb = 0; kb < kb_n; ++kb) {
         mbar_wait(&empty[st.stage], st.phase ^ 1);
         mbar_arrive_expect_tx(&full[st.stage], kTileA + b_bytes * (SPLIT ? 2u : 1u));
-        // panels: tile (panel kb, rows mblk*BM..) is one contiguous 16 KiB run (panels are zero-padded to a multiple of 128 rows)
-        const int kbe = P.krot ? (kb + (int)blockIdx.x) % kb_n : kb;   // which k-block this stage holds (the sum over k is order-free)
-        if (P.prob[p].panel) tma_load_2d(sA(st.stage), &P.tmA[p], &full[st.stage], 0, kbe * P.prob[p].panel + mblk * BM);
-        else tma_load_2d(sA(st.stage), &P.tmA[p], &full[st.stage], kbe * BK, mblk * BM);
+        const int kbe = kb;
+        tma_load_2d(sA(st.stage), &P.tmA[p], &full[st.stage], kbe * BK, mblk * BM);
         tma_load_2d(sB(st.stage), &P.tmW[p], &full[st.stage], kbe * BK, 0);
-        if (SPLIT && !P.wbox) tma_load_2d(sBlo(st.stage), &P.tmW[p], &full[st.stage], kbe * BK, d);
+        if (SPLIT) tma_load_2d(sBlo(st.stage), &P.tmW[p], &full[st.stage], kbe * BK, d);
         st.advance();
       }
     }
@@ -320,9 +318,7 @@ __global__ void __launch_bounds__(384, 1) proj_wgrad_tc_kernel(const __grid_cons
         const int r = r0 + kb * BK;
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
-          // panels: one contiguous 4 KiB run per box; rows past n are the panel's zero padding, panels past k/32 are out of bounds (zero fill)
-          if (P.prob[p].panel) tma_load_2d(sA(st.stage) + a * 4096, &P.tmX[p], &full[st.stage], 0, (ft * 4 + a) * P.prob[p].panel + r);
-          else tma_load_2d(sA(st.stage) + a * 4096, &P.tmX[p], &full[st.stage], ft * BM + a * 32, r);
+          tma_load_2d(sA(st.stage) + a * 4096, &P.tmX[p], &full[st.stage], ft * BM + a * 32, r);
         }
         for (int b = 0; b < d / 32; ++b) tma_load_2d(sB(st.stage) + b * 4096, &P.tmG[p], &full[st.stage], b * 32, r);
         st.advance();
@@ -516,9 +512,6 @@ int proj_fwd_tc_group(const llmrec_proj_fwd_problem* pr, int n_prob, int d, int 
   memset(&P, 0, sizeof(P));
   P.n_prob = n_prob; P.d = d;
   int tiles = 0;
-  static const bool wbox_env = getenv("LLMREC_PROJ_WBOX") != nullptr;
-  const bool wbox = wbox_env && split && 2 * d <= 256;          // TMA boxes hold at most 256 rows
-  P.wbox = wbox ? 1 : 0;
   for (int p = 0; p < n_prob; ++p) {
     const float* wsrc = split ? pr[p].wsplit : pr[p].W;
     LLMREC_CHECK_ARG(!split || pr[p].wsplit, "proj_fwd: 3xTF32 mode needs a wsplit buffer of 2*d*k floats");
@@ -529,31 +522,21 @@ int proj_fwd_tc_group(const llmrec_proj_fwd_problem* pr, int n_prob, int d, int 
       wsplit_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pr[p].W, pr[p].wsplit, n);
       LLMREC_CHECK_LAUNCH("wsplit");
     }
-    const bool panel = pr[p].x_layout == LLMREC_X_PANELS;
-    const int64_t npad = LLMREC_PANEL_ROWS(pr[p].n);
-    if (panel) {
-      LLMREC_CHECK_ARG(pr[p].k % BK == 0 && (int64_t)(pr[p].k / BK) * npad < (int64_t)INT32_MAX, "proj_fwd: panel layout needs k %% 32 == 0 and (k/32)*n < 2^31");
-      if (!make_tmap_2d_f32(&P.tmA[p], pr[p].X, (uint64_t)BK, (uint64_t)(pr[p].k / BK) * (uint64_t)npad, (uint64_t)BK * 4, BK, BM)) return 4;
-    } else if (!make_tmap_2d_f32(&P.tmA[p], pr[p].X, (uint64_t)pr[p].k, (uint64_t)pr[p].n, (uint64_t)pr[p].ldx * 4, BK, BM)) return 4;
-    P.prob[p].panel = panel ? (int)npad : 0;
-    if (!make_tmap_2d_f32(&P.tmW[p], wsrc, (uint64_t)pr[p].k, (uint64_t)(split ? 2 * d : d), (uint64_t)pr[p].k * 4, BK, (uint32_t)(wbox ? 2 * d : d))) return 4;
+    if (!make_tmap_2d_f32(&P.tmA[p], pr[p].X, (uint64_t)pr[p].k, (uint64_t)pr[p].n, (uint64_t)pr[p].ldx * 4, BK, BM)) return 4;
+    if (!make_tmap_2d_f32(&P.tmW[p], wsrc, (uint64_t)pr[p].k, (uint64_t)(split ? 2 * d : d), (uint64_t)pr[p].k * 4, BK, (uint32_t)d)) return 4;
     P.prob[p].n = (int)pr[p].n; P.prob[p].k = pr[p].k; P.prob[p].kblocks = (pr[p].k + BK - 1) / BK;
     P.prob[p].tile_start = tiles; P.prob[p].ldy = pr[p].ldy; P.prob[p].Y = pr[p].Y; P.prob[p].bias = pr[p].bias;
     tiles += (int)((pr[p].n + BM - 1) / BM);
   }
   P.total_tiles = tiles;
-  static const bool krot = getenv("LLMREC_PROJ_KROT") != nullptr;
-  P.krot = krot ? 1 : 0;
-  static const int skipw = getenv("LLMREC_PROJ_SKIPW") ? atoi(getenv("LLMREC_PROJ_SKIPW")) : 0;   // TIMING experiments (wrong results): 1 no W loads, 2 no MMAs, 4 no transform
-  P.skipw = skipw;
+  static const int dbg = getenv("LLMREC_PROJ_DBG") ? atoi(getenv("LLMREC_PROJ_DBG")) : 0;   // TIMING experiments (wrong results): 1 no W loads, 2 no MMAs, 4 no transform
+  P.dbg = dbg;
   uint32_t smem;
   P.stages = stages_for(d, split, &smem);
   P.tmem_cols = (int)pow2_cols(2 * d);
   int grid = tiles < 148 ? tiles : 148;
   if (grid <= 0) return 0;
   static const bool force_v1 = getenv("LLMREC_PROJ_V1") != nullptr;
-  static const int fwd_v = getenv("LLMREC_PROJ_FWD_V") ? atoi(getenv("LLMREC_PROJ_FWD_V")) : 3;
-  if (split && d <= 128 && !force_v1 && fwd_v == 3 && !wbox) return proj_fwd_ts3_launch(P, grid, st);   // decoupled A / W / TMEM rings (proj_tc2.cu)
   if (split && d <= 128 && !force_v1) return proj_fwd_ts_launch(P, grid, st);   // A operand from tensor memory (proj_tc2.cu)
   if (split) {
     cudaFuncSetAttribute(proj_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -567,8 +550,7 @@ int proj_fwd_tc_group(const llmrec_proj_fwd_problem* pr, int n_prob, int d, int 
 }
 
 static int wg_rows_per_chunk(int64_t n) {
-  static const int env = getenv("LLMREC_WG_ROWS") ? atoi(getenv("LLMREC_WG_ROWS")) : 0;   // experiment: rows per work item (multiple of 32)
-  int r = (env >= 256 && env % 32 == 0) ? env : 2048;
+  int r = 2048;                       // rows per work item (1024 / 4096 measured: no better)
   while (r > 256 && n / r < 4) r >>= 1;
   return r;
 }
@@ -592,28 +574,13 @@ int proj_wgrad_tc_group(const llmrec_proj_wgrad_problem* pr, int n_prob, int d, 
   memset(&C, 0, sizeof(C));
   C.d = d;
   for (int p = 0; p < n_prob; ++p) {
-    const bool panel = (pr[p].accumulate & LLMREC_WGRAD_X_PANELS) != 0;
-    const int64_t npad = LLMREC_PANEL_ROWS(pr[p].n);
-    if (panel) {
-      LLMREC_CHECK_ARG(pr[p].k % BK == 0 && (int64_t)(pr[p].k / BK + 4) * npad < (int64_t)INT32_MAX, "proj_wgrad: panel layout needs k %% 32 == 0 and (k/32 + 4)*n < 2^31");
-      if (!make_tmap_2d_f32(&P.tmX[p], pr[p].X, (uint64_t)32, (uint64_t)(pr[p].k / 32) * (uint64_t)npad, (uint64_t)128, 32, BK, true)) return 4;
-    } else if (!make_tmap_2d_f32(&P.tmX[p], pr[p].X, (uint64_t)pr[p].k, (uint64_t)pr[p].n, (uint64_t)pr[p].ldx * 4, 32, BK, true)) return 4;
-    // experiments (v2 kernel only): one rank-3 box per operand tile instead of 4 + d/32 rank-2 boxes
-    static const bool x3d_env = getenv("LLMREC_PROJ_X3D") != nullptr, g3d_env = getenv("LLMREC_PROJ_G3D") != nullptr;
-    const bool ts = split && d <= 128 && getenv("LLMREC_PROJ_V1") == nullptr;
-    const bool x3d = x3d_env && panel && ts, g3d = g3d_env && ts;
-    if (x3d && !make_tmap_3d_f32(&P.tmX[p], pr[p].X, 32, (uint64_t)npad, (uint64_t)(pr[p].k / 32), 128, (uint64_t)npad * 128, 32, BK, 4)) return 4;
-    if (g3d) {
-      if (!make_tmap_3d_f32(&P.tmG[p], pr[p].dY, 32, (uint64_t)pr[p].n, (uint64_t)(d / 32), (uint64_t)pr[p].lddy * 4, 128, 32, BK, (uint32_t)(d / 32))) return 4;
-    } else
+    if (!make_tmap_2d_f32(&P.tmX[p], pr[p].X, (uint64_t)pr[p].k, (uint64_t)pr[p].n, (uint64_t)pr[p].ldx * 4, 32, BK, true)) return 4;
     if (!make_tmap_2d_f32(&P.tmG[p], pr[p].dY, (uint64_t)d, (uint64_t)pr[p].n, (uint64_t)pr[p].lddy * 4, 32, BK, true)) return 4;
     WgProblem& w = P.prob[p];
     w.n = (int)pr[p].n; w.k = pr[p].k; w.ft_tiles = (pr[p].k + BM - 1) / BM;
     w.rows_per_chunk = wg_rows_per_chunk(pr[p].n);
     w.chunks = (int)((pr[p].n + w.rows_per_chunk - 1) / w.rows_per_chunk);
     w.item_start = items;
-    w.panel = panel ? (int)npad : 0;
-    w.x3d = x3d ? 1 : 0; w.g3d = g3d ? 1 : 0;
     items += w.ft_tiles * w.chunks;
     C.dY[p] = pr[p].dY; C.ld[p] = pr[p].lddy; C.n[p] = pr[p].n; C.db[p] = pr[p].db; C.acc[p] = pr[p].accumulate & LLMREC_WGRAD_ACCUMULATE;
   }
@@ -628,11 +595,8 @@ int proj_wgrad_tc_group(const llmrec_proj_wgrad_problem* pr, int n_prob, int d, 
   int grid = items < 148 ? items : 148;
   if (grid <= 0) return 0;
   static const bool force_v1 = getenv("LLMREC_PROJ_V1") != nullptr;
-  static const int wg_v = getenv("LLMREC_PROJ_WG_V") ? atoi(getenv("LLMREC_PROJ_WG_V")) : 3;
-  bool any3d = false;
-  for (int p = 0; p < n_prob; ++p) any3d = any3d || P.prob[p].x3d || P.prob[p].g3d;
   if (split && d <= 128 && !force_v1) {
-    int rc = (wg_v == 3 && !any3d) ? proj_wgrad_ts3_launch(P, grid, st) : proj_wgrad_ts_launch(P, grid, st);   // decoupled X / dY / TMEM rings vs v2
+    int rc = proj_wgrad_ts_launch(P, grid, st);
     if (rc) return rc;
   } else if (split) {
     cudaFuncSetAttribute(proj_wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

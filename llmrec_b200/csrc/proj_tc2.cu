@@ -68,14 +68,11 @@ __global__ void __launch_bounds__(512, 1) proj_fwd_ts_kernel(const __grid_consta
       const int kb_n = P.prob[p].kblocks;
       for (int kb = 0; kb < kb_n; ++kb) {
         mbar_wait(&empty[st.stage], st.phase ^ 1);
-        mbar_arrive_expect_tx(&full[st.stage], (P.skipw & 1) ? kTileA : stage_bytes);
-        // panels: tile (panel kb, rows mblk*BM..) is one contiguous 16 KiB run (panels are zero-padded to a multiple of 128 rows)
-        const int kbe = P.krot ? (kb + (int)blockIdx.x) % kb_n : kb;   // which k-block this stage holds (the sum over k is order-free)
-        if (P.prob[p].panel) tma_load_2d(sA(st.stage), &P.tmA[p], &full[st.stage], 0, kbe * P.prob[p].panel + mblk * BM);
-        else tma_load_2d(sA(st.stage), &P.tmA[p], &full[st.stage], kbe * BK, mblk * BM);
-        if (!(P.skipw & 1)) {
-          tma_load_2d(sB(st.stage), &P.tmW[p], &full[st.stage], kbe * BK, 0);      // wbox: this one box is [2d x 32] = W_hi | W_lo
-          if (!P.wbox) tma_load_2d(sBlo(st.stage), &P.tmW[p], &full[st.stage], kbe * BK, d);
+        mbar_arrive_expect_tx(&full[st.stage], (P.dbg & 1) ? kTileA : stage_bytes);
+        tma_load_2d(sA(st.stage), &P.tmA[p], &full[st.stage], kb * BK, mblk * BM);
+        if (!(P.dbg & 1)) {
+          tma_load_2d(sB(st.stage), &P.tmW[p], &full[st.stage], kb * BK, 0);
+          tma_load_2d(sBlo(st.stage), &P.tmW[p], &full[st.stage], kb * BK, d);
         }
         st.advance();
       }
@@ -95,7 +92,7 @@ __global__ void __launch_bounds__(512, 1) proj_fwd_ts_kernel(const __grid_consta
         tc_fence_after();
         const uint32_t b0 = smem_u32(sB(st.stage)), bl0 = smem_u32(sBlo(st.stage));
         const uint32_t a_hi = tmem_base + a_col0 + (uint32_t)(st.stage * kSlotCols), a_lo = a_hi + 32;
-        if (!(P.skipw & 2)) {
+        if (!(P.dbg & 2)) {
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           const uint64_t bd = smem_desc_sw128(b0 + kk * 32, 0, 1024);
@@ -128,7 +125,7 @@ __global__ void __launch_bounds__(512, 1) proj_fwd_ts_kernel(const __grid_consta
         const int stage = (int)(it % stages);
         const uint32_t phase = (it / stages) & 1u;
         mbar_wait(&full[stage], phase);
-        if (P.skipw & 4) { __syncwarp(); if (lane == 0) mbar_arrive(&xform[stage]); continue; }   // timing experiment: no transform work
+        if (P.dbg & 4) { __syncwarp(); if (lane == 0) mbar_arrive(&xform[stage]); continue; }   // timing experiment: no transform work
         const uint8_t* rowp = sA(stage) + (size_t)row * 128;
         uint32_t hi[32], lo[32];
 #pragma unroll
@@ -145,201 +142,6 @@ __global__ void __launch_bounds__(512, 1) proj_fwd_ts_kernel(const __grid_consta
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&xform[stage]);
-      }
-    }
-  } else if (warp >= 8 && warp < 12) {
-    const int wq = warp & 3;
-    int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-      int p, mblk; locate(tile, p, mblk);
-      const FwdProblem pr = P.prob[p];
-      mbar_wait(&tfull[acc], acc_phase);
-      tc_fence_after();
-      const int row = mblk * BM + wq * 32 + lane;
-      const uint32_t t0 = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * d);
-      float* yrow = pr.Y + (long long)row * pr.ldy;
-      int c0 = 0;
-      for (; c0 + 32 <= d; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(t0 + c0, r);
-        tmem_ld_wait();
-        if (row < pr.n) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 b = pr.bias ? __ldg(reinterpret_cast<const float4*>(pr.bias + c0 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            st4(yrow + c0 + j, make_float4(__uint_as_float(r[j]) + b.x, __uint_as_float(r[j + 1]) + b.y,
-                                           __uint_as_float(r[j + 2]) + b.z, __uint_as_float(r[j + 3]) + b.w));
-          }
-        }
-      }
-      if (c0 < d) {  // d % 32 == 16
-        uint32_t r[16];
-        tmem_ld_32x16(t0 + c0, r);
-        tmem_ld_wait();
-        if (row < pr.n) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            float4 b = pr.bias ? __ldg(reinterpret_cast<const float4*>(pr.bias + c0 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            st4(yrow + c0 + j, make_float4(__uint_as_float(r[j]) + b.x, __uint_as_float(r[j + 1]) + b.y,
-                                           __uint_as_float(r[j + 2]) + b.z, __uint_as_float(r[j + 3]) + b.w));
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512u); }
-}
-
-// ---- forward, third generation: THREE DECOUPLED RINGS ------------------------------------------------------------------------------
-// v2 ties one smem stage (A 16 KiB + W_hi/W_lo 2 x d x 128 B) to one TMEM slot and frees it only when its MMAs retire: 6 stages = 96 KiB of
-// feature bytes in flight per SM, and a stage is held ~5000 clk (loaded DRAM latency ~3600 clk + transform + MMA + barrier hops) -- the
-// kernel is bound by bytes in flight, not by HBM, tensor pipe or the transform (ncu: transform warps wait on `full` 31 % of samples).
-// Here the three resources have the lifetimes they need:
-//   A ring  (smem, 10-12 x 16 KiB)  TMA -> [full_a] -> transform reads the tile into registers -> [empty_a]   (freed BEFORE the MMAs)
-//   T ring  (TMEM, 4-6 x 64 columns) transform stores hi|lo -> [xform] -> MMAs -> tcgen05.commit -> [t_empty]
-//   W ring  (smem, 2-3 x 2d x 128 B) own producer (warp 3), L2-resident operand -> [full_w] -> MMAs -> commit -> [empty_w]
-// so ~176 KiB of the feature stream is in flight per SM with the same 227 KiB of shared memory.  Roles otherwise as v2.
-__global__ void __launch_bounds__(512, 1) proj_fwd_ts3_kernel(const __grid_constant__ FwdParams P) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int d = P.d;
-  const int NA = P.stages, NW = P.nw, NT = P.nt;
-  const uint32_t b_bytes = (uint32_t)d * 128u;
-  const uint32_t w_bytes = 2u * b_bytes;                        // W_hi | W_lo of one k-block
-  uint8_t* aring = smem;
-  uint8_t* wring = smem + (size_t)NA * kTileA;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(wring + (size_t)NW * w_bytes);
-  uint64_t* full_a = bars; uint64_t* empty_a = full_a + NA;
-  uint64_t* full_w = empty_a + NA; uint64_t* empty_w = full_w + NW;
-  uint64_t* xform = empty_w + NW; uint64_t* t_empty = xform + NT;
-  uint64_t* tfull = t_empty + NT; uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  auto sA = [&](int s) { return aring + (size_t)s * kTileA; };
-  auto sW = [&](int s) { return wring + (size_t)s * w_bytes; };
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 0 && lane == 0) {
-    for (int p = 0; p < P.n_prob; ++p) { prefetch_tmap(&P.tmA[p]); prefetch_tmap(&P.tmW[p]); }
-  }
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < NA; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 4); }
-    for (int s = 0; s < NW; ++s) { mbar_init(&full_w[s], 1); mbar_init(&empty_w[s], 1); }
-    for (int s = 0; s < NT; ++s) { mbar_init(&xform[s], 4); mbar_init(&t_empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc(tmem_slot, 512u);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t a_col0 = 2u * (uint32_t)d;  // [0, 2d) accumulators | [2d, 2d + NT*64) A ring
-
-  auto locate = [&](int tile, int& p, int& mblk) {
-    p = 0;
-    while (p + 1 < P.n_prob && tile >= P.prob[p + 1].tile_start) ++p;
-    mblk = tile - P.prob[p].tile_start;
-  };
-
-  if (warp == 0 && lane == 0) {
-    // ===== A producer: runs as far ahead as the A ring allows =====
-    PipeState st(NA);
-    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-      int p, mblk; locate(tile, p, mblk);
-      const int kb_n = P.prob[p].kblocks;
-      for (int kb = 0; kb < kb_n; ++kb) {
-        mbar_wait(&empty_a[st.stage], st.phase ^ 1);
-        mbar_arrive_expect_tx(&full_a[st.stage], kTileA);
-        if (P.prob[p].panel) tma_load_2d(sA(st.stage), &P.tmA[p], &full_a[st.stage], 0, kb * P.prob[p].panel + mblk * BM);
-        else tma_load_2d(sA(st.stage), &P.tmA[p], &full_a[st.stage], kb * BK, mblk * BM);
-        st.advance();
-      }
-    }
-  } else if (warp == 3 && lane == 0) {
-    // ===== W producer (L2-resident operand; only has to stay a k-block or two ahead of the MMAs) =====
-    PipeState st(NW);
-    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-      int p, mblk; locate(tile, p, mblk);
-      const int kb_n = P.prob[p].kblocks;
-      for (int kb = 0; kb < kb_n; ++kb) {
-        mbar_wait(&empty_w[st.stage], st.phase ^ 1);
-        mbar_arrive_expect_tx(&full_w[st.stage], w_bytes);
-        tma_load_2d(sW(st.stage), &P.tmW[p], &full_w[st.stage], kb * BK, 0);
-        tma_load_2d(sW(st.stage) + b_bytes, &P.tmW[p], &full_w[st.stage], kb * BK, d);
-        st.advance();
-      }
-    }
-  } else if (warp == 1 && lane == 0) {
-    PipeState tt(NT), sw(NW);
-    const uint32_t idesc = idesc_tf32(BM, d, 0, 0);
-    int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-      int p, mblk; locate(tile, p, mblk);
-      const int kb_n = P.prob[p].kblocks;
-      mbar_wait(&tempty[acc], acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * d);
-      for (int kb = 0; kb < kb_n; ++kb) {
-        mbar_wait(&full_w[sw.stage], sw.phase);
-        mbar_wait(&xform[tt.stage], tt.phase);
-        tc_fence_after();
-        const uint32_t b0 = smem_u32(sW(sw.stage)), bl0 = b0 + b_bytes;
-        const uint32_t a_hi = tmem_base + a_col0 + (uint32_t)(tt.stage * kSlotCols), a_lo = a_hi + 32;
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          const uint64_t bd = smem_desc_sw128(b0 + kk * 32, 0, 1024);
-          const uint64_t bld = smem_desc_sw128(bl0 + kk * 32, 0, 1024);
-          umma_tf32_ts(d_tmem, a_lo + kk * 8, bd, idesc, (kb | kk) != 0);   // lo * hi
-          umma_tf32_ts(d_tmem, a_hi + kk * 8, bld, idesc, 1);                // hi * lo
-          umma_tf32_ts(d_tmem, a_hi + kk * 8, bd, idesc, 1);                 // hi * hi
-        }
-        umma_commit(&t_empty[tt.stage]);
-        umma_commit(&empty_w[sw.stage]);
-        tt.advance(); sw.advance();
-      }
-      umma_commit(&tfull[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    }
-  } else if ((warp >= 4 && warp < 8) || warp >= 12) {
-    // ===== transform: smem A row -> registers (A slot released) -> split -> TMEM slot =====
-    const int grp = warp >= 12 ? 1 : 0;
-    const int wq = warp & 3;
-    const int row = wq * 32 + lane;
-    const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16) + a_col0;
-    uint32_t it = 0;   // running k-block counter over all tiles of this CTA
-    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-      int p, mblk; locate(tile, p, mblk);
-      const int kb_n = P.prob[p].kblocks;
-      for (int kb = 0; kb < kb_n; ++kb, ++it) {
-        if ((int)(it & 1u) != grp) continue;
-        const int sa = (int)(it % (uint32_t)NA), ts = (int)(it % (uint32_t)NT);
-        mbar_wait(&full_a[sa], (it / (uint32_t)NA) & 1u);
-        const uint8_t* rowp = sA(sa) + (size_t)row * 128;
-        uint32_t hi[32], lo[32];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {  // logical 16-byte chunk c sits at physical chunk c ^ (row & 7) (SWIZZLE_128B)
-          const float4 v = *reinterpret_cast<const float4*>(rowp + ((c ^ (row & 7)) << 4));
-          const float h0 = tf32_hi(v.x), h1 = tf32_hi(v.y), h2 = tf32_hi(v.z), h3 = tf32_hi(v.w);
-          hi[4 * c] = __float_as_uint(h0); hi[4 * c + 1] = __float_as_uint(h1); hi[4 * c + 2] = __float_as_uint(h2); hi[4 * c + 3] = __float_as_uint(h3);
-          lo[4 * c] = __float_as_uint(v.x - h0); lo[4 * c + 1] = __float_as_uint(v.y - h1);
-          lo[4 * c + 2] = __float_as_uint(v.z - h2); lo[4 * c + 3] = __float_as_uint(v.w - h3);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_a[sa]);                   // the tile lives in registers now: its smem slot can be refilled
-        mbar_wait(&t_empty[ts], ((it / (uint32_t)NT) & 1u) ^ 1u);   // the MMAs that read this TMEM slot last time have retired
-        tc_fence_after();
-        tmem_st_32x32(lane_base + (uint32_t)(ts * kSlotCols), hi);
-        tmem_st_32x32(lane_base + (uint32_t)(ts * kSlotCols + 32), lo);
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&xform[ts]);
       }
     }
   } else if (warp >= 8 && warp < 12) {
@@ -443,19 +245,9 @@ __global__ void __launch_bounds__(512, 1) proj_wgrad_ts_kernel(const __grid_cons
         mbar_wait(&empty[st.stage], st.phase ^ 1);
         mbar_arrive_expect_tx(&full[st.stage], kTileA + b_bytes);
         const int r = r0 + kb * BK;
-        if (P.prob[p].x3d) {
-          // panels as a rank-3 tensor (32 floats, rows, panels): ONE box = 4 panels x 32 rows, landing as the same four 4 KiB atoms
-          tma_load_3d(sA(st.stage), &P.tmX[p], &full[st.stage], 0, r, ft * 4);
-        } else {
 #pragma unroll
-          for (int a = 0; a < 4; ++a) {
-            // panels: one contiguous 4 KiB run per box; rows past n are the panel's zero padding, panels past k/32 are out of bounds (zero fill)
-            if (P.prob[p].panel) tma_load_2d(sA(st.stage) + a * 4096, &P.tmX[p], &full[st.stage], 0, (ft * 4 + a) * P.prob[p].panel + r);
-            else tma_load_2d(sA(st.stage) + a * 4096, &P.tmX[p], &full[st.stage], ft * BM + a * 32, r);
-          }
-        }
-        if (P.prob[p].g3d) tma_load_3d(sB(st.stage), &P.tmG[p], &full[st.stage], 0, r, 0);   // (32 floats, rows, d/32 column blocks) in one box
-        else for (int b = 0; b < d / 32; ++b) tma_load_2d(sB(st.stage) + b * 4096, &P.tmG[p], &full[st.stage], b * 32, r);
+        for (int a = 0; a < 4; ++a) tma_load_2d(sA(st.stage) + a * 4096, &P.tmX[p], &full[st.stage], ft * BM + a * 32, r);
+        for (int b = 0; b < d / 32; ++b) tma_load_2d(sB(st.stage) + b * 4096, &P.tmG[p], &full[st.stage], b * 32, r);
         st.advance();
       }
     }
@@ -548,178 +340,6 @@ __global__ void __launch_bounds__(512, 1) proj_wgrad_ts_kernel(const __grid_cons
   if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512u); }
 }
 
-// ---- wgrad, third generation: the same three decoupled rings (X tiles | TMEM A slots | dY tiles) ------------------------------------
-// The dY tile of a k-block (fp32, [32 rows x d]) arrives in its own ring, is split hi | lo IN PLACE by the transform group that also
-// moves the X tile into TMEM, and is released by the commit of the MMAs that read it; the X slot is released as soon as the tile is in
-// registers.  See proj_fwd_ts3_kernel for the lifetimes.
-__global__ void __launch_bounds__(512, 1) proj_wgrad_ts3_kernel(const __grid_constant__ WgParams P) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int d = P.d;
-  const int NA = P.stages, NG = P.ng, NT = P.nt;
-  const uint32_t b_bytes = (uint32_t)d * 128u;                  // [d/32 atoms][32 rows][128 B]
-  const uint32_t g_bytes = 2u * b_bytes;                        // dY_hi (in place) | dY_lo
-  uint8_t* aring = smem;
-  uint8_t* gring = smem + (size_t)NA * kTileA;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(gring + (size_t)NG * g_bytes);
-  uint64_t* full_a = bars; uint64_t* empty_a = full_a + NA;
-  uint64_t* full_g = empty_a + NA; uint64_t* empty_g = full_g + NG;
-  uint64_t* xform = empty_g + NG; uint64_t* t_empty = xform + NT;
-  uint64_t* tfull = t_empty + NT; uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  auto sA = [&](int s) { return aring + (size_t)s * kTileA; };
-  auto sG = [&](int s) { return gring + (size_t)s * g_bytes; };
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 0 && lane == 0) {
-    for (int p = 0; p < P.n_prob; ++p) { prefetch_tmap(&P.tmX[p]); prefetch_tmap(&P.tmG[p]); }
-  }
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < NA; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 4); }
-    for (int s = 0; s < NG; ++s) { mbar_init(&full_g[s], 1); mbar_init(&empty_g[s], 1); }
-    for (int s = 0; s < NT; ++s) { mbar_init(&xform[s], 4); mbar_init(&t_empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc(tmem_slot, 512u);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t a_col0 = 2u * (uint32_t)d;
-
-  auto locate = [&](int item, int& p, int& ft, int& r0, int& kb_n) {
-    p = 0;
-    while (p + 1 < P.n_prob && item >= P.prob[p + 1].item_start) ++p;
-    const WgProblem pr = P.prob[p];
-    const int local = item - pr.item_start;
-    const int chunk = local / pr.ft_tiles;
-    ft = local - chunk * pr.ft_tiles;
-    r0 = chunk * pr.rows_per_chunk;
-    const int r1 = min(pr.n, r0 + pr.rows_per_chunk);
-    kb_n = (r1 - r0 + BK - 1) / BK;
-  };
-
-  if (warp == 0 && lane == 0) {
-    PipeState st(NA);
-    for (int item = blockIdx.x; item < P.total_items; item += gridDim.x) {
-      int p, ft, r0, kb_n; locate(item, p, ft, r0, kb_n);
-      for (int kb = 0; kb < kb_n; ++kb) {
-        mbar_wait(&empty_a[st.stage], st.phase ^ 1);
-        mbar_arrive_expect_tx(&full_a[st.stage], kTileA);
-        const int r = r0 + kb * BK;
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          if (P.prob[p].panel) tma_load_2d(sA(st.stage) + a * 4096, &P.tmX[p], &full_a[st.stage], 0, (ft * 4 + a) * P.prob[p].panel + r);
-          else tma_load_2d(sA(st.stage) + a * 4096, &P.tmX[p], &full_a[st.stage], ft * BM + a * 32, r);
-        }
-        st.advance();
-      }
-    }
-  } else if (warp == 3 && lane == 0) {
-    PipeState st(NG);
-    for (int item = blockIdx.x; item < P.total_items; item += gridDim.x) {
-      int p, ft, r0, kb_n; locate(item, p, ft, r0, kb_n);
-      for (int kb = 0; kb < kb_n; ++kb) {
-        mbar_wait(&empty_g[st.stage], st.phase ^ 1);
-        mbar_arrive_expect_tx(&full_g[st.stage], b_bytes);
-        const int r = r0 + kb * BK;
-        for (int b = 0; b < d / 32; ++b) tma_load_2d(sG(st.stage) + b * 4096, &P.tmG[p], &full_g[st.stage], b * 32, r);
-        st.advance();
-      }
-    }
-  } else if (warp == 1 && lane == 0) {
-    PipeState tt(NT), sg(NG);
-    const uint32_t idesc = idesc_tf32(BM, d, 0, 1);   // A: TMEM (lane = M, column = K); B: MN-major in smem
-    int acc = 0; uint32_t acc_phase = 0;
-    for (int item = blockIdx.x; item < P.total_items; item += gridDim.x) {
-      int p, ft, r0, kb_n; locate(item, p, ft, r0, kb_n);
-      mbar_wait(&tempty[acc], acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * d);
-      for (int kb = 0; kb < kb_n; ++kb) {
-        mbar_wait(&xform[tt.stage], tt.phase);        // X tile in TMEM AND the dY tile of this k-block split in place
-        tc_fence_after();
-        const uint32_t b0 = smem_u32(sG(sg.stage)), bl0 = b0 + b_bytes;
-        const uint32_t a_hi = tmem_base + a_col0 + (uint32_t)(tt.stage * kSlotCols), a_lo = a_hi + 32;
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {  // 8 rows per MMA: TMEM columns kk*8.., smem B advances 8 rows = 1024 B
-          const uint64_t bd = smem_desc_sw128(b0 + kk * 1024, 4096, 512, 1);
-          const uint64_t bld = smem_desc_sw128(bl0 + kk * 1024, 4096, 512, 1);
-          umma_tf32_ts(d_tmem, a_lo + kk * 8, bd, idesc, (kb | kk) != 0);
-          umma_tf32_ts(d_tmem, a_hi + kk * 8, bld, idesc, 1);
-          umma_tf32_ts(d_tmem, a_hi + kk * 8, bd, idesc, 1);
-        }
-        umma_commit(&t_empty[tt.stage]);
-        umma_commit(&empty_g[sg.stage]);
-        tt.advance(); sg.advance();
-      }
-      umma_commit(&tfull[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    }
-  } else if ((warp >= 4 && warp < 8) || warp >= 12) {
-    const int grp = warp >= 12 ? 1 : 0;
-    const int wq = warp & 3;                          // feature atom: features [32*wq, 32*wq + 32)
-    const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16) + a_col0;
-    const int tid = (warp & 3) * 32 + lane;
-    uint32_t it = 0;
-    for (int item = blockIdx.x; item < P.total_items; item += gridDim.x) {
-      int p, ft, r0, kb_n; locate(item, p, ft, r0, kb_n);
-      for (int kb = 0; kb < kb_n; ++kb, ++it) {
-        if ((int)(it & 1u) != grp) continue;
-        const int sa = (int)(it % (uint32_t)NA), ts = (int)(it % (uint32_t)NT), gs = (int)(it % (uint32_t)NG);
-        mbar_wait(&full_a[sa], (it / (uint32_t)NA) & 1u);
-        // element (row r, feature e = lane) of atom wq: byte r*128 + (((e >> 3) ^ (r & 3)) << 5) + (e & 7)*4   (SWIZZLE_128B_ATOM_32B)
-        const uint8_t* atom = sA(sa) + (size_t)wq * 4096;
-        uint32_t hi[32], lo[32];
-#pragma unroll
-        for (int r = 0; r < 32; ++r) {
-          const float v = *reinterpret_cast<const float*>(atom + r * 128 + ((((lane >> 3) ^ (r & 3)) << 5) | ((lane & 7) << 2)));
-          const float h = tf32_hi(v);
-          hi[r] = __float_as_uint(h); lo[r] = __float_as_uint(v - h);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_a[sa]);                    // X tile is in registers: release its smem slot
-        mbar_wait(&full_g[gs], (it / (uint32_t)NG) & 1u);
-        split_tile_inplace(reinterpret_cast<float4*>(sG(gs)), reinterpret_cast<float4*>(sG(gs) + b_bytes), (int)(b_bytes / 16), tid, 128);
-        fence_proxy_async_smem();
-        mbar_wait(&t_empty[ts], ((it / (uint32_t)NT) & 1u) ^ 1u);
-        tc_fence_after();
-        tmem_st_32x32(lane_base + (uint32_t)(ts * kSlotCols), hi);
-        tmem_st_32x32(lane_base + (uint32_t)(ts * kSlotCols + 32), lo);
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&xform[ts]);
-      }
-    }
-  } else if (warp >= 8 && warp < 12) {
-    const int wq = warp & 3;
-    int acc = 0; uint32_t acc_phase = 0;
-    for (int item = blockIdx.x; item < P.total_items; item += gridDim.x) {
-      mbar_wait(&tfull[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t t0 = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * d);
-      float* out = P.partial + ((long long)item * BM + wq * 32 + lane) * d;
-      for (int c0 = 0; c0 < d; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(t0 + c0, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          st4(out + c0 + j, make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512u); }
-}
-
 // The ring must cover HBM latency + transform + MMA time of a stage (~2900 clk): 4 stages of 16 KiB sustain only ~3.5 TB/s.
 static int ts_stages(int d) { return d <= 64 ? kTsMaxStages : 4; }
 static uint32_t ts_smem_bytes(int d) { return (uint32_t)ts_stages(d) * (kTileA + 2u * (uint32_t)d * 128u) + 1024 + 256; }
@@ -731,42 +351,6 @@ int proj_fwd_ts_launch(const FwdParams& P0, int grid, cudaStream_t st) {
   cudaFuncSetAttribute(proj_fwd_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   proj_fwd_ts_kernel<<<grid, 512, smem, st>>>(P);
   LLMREC_CHECK_LAUNCH("proj_fwd_ts");
-  return 0;
-}
-int proj_fwd_ts3_launch(const FwdParams& P0, int grid, cudaStream_t st) {
-  FwdParams P = P0;
-  const uint32_t w_bytes = 2u * (uint32_t)P.d * 128u;
-  P.nt = (512 - 2 * P.d) / kSlotCols; if (P.nt > 6) P.nt = 6;
-  // a W slot is held from its TMA issue until the COMMIT of the MMAs that read it (L2 latency + queueing + MMA + commit latency, ~4000 clk):
-  // it needs about as many slots as the A ring (measured: 3 W slots throttle the kernel below v2)
-  static const int nw_env = getenv("LLMREC_PROJ_NW") ? atoi(getenv("LLMREC_PROJ_NW")) : 0;
-  P.nw = nw_env > 0 ? nw_env : (P.d <= 64 ? 6 : 4);
-  const uint32_t budget = 232448u - 1024u /*align*/ - 1024u /*barriers*/;
-  int na = (int)((budget - (uint32_t)P.nw * w_bytes) / kTileA);
-  if (na > 12) na = 12;
-  if (na < 2) return proj_fwd_ts_launch(P0, grid, st);
-  P.stages = na;
-  const uint32_t smem = (uint32_t)na * kTileA + (uint32_t)P.nw * w_bytes + 1024 + 1024;
-  cudaFuncSetAttribute(proj_fwd_ts3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  proj_fwd_ts3_kernel<<<grid, 512, smem, st>>>(P);
-  LLMREC_CHECK_LAUNCH("proj_fwd_ts3");
-  return 0;
-}
-int proj_wgrad_ts3_launch(const WgParams& P0, int grid, cudaStream_t st) {
-  WgParams P = P0;
-  const uint32_t g_bytes = 2u * (uint32_t)P.d * 128u;
-  P.nt = (512 - 2 * P.d) / kSlotCols; if (P.nt > 6) P.nt = 6;
-  static const int ng_env = getenv("LLMREC_PROJ_NW") ? atoi(getenv("LLMREC_PROJ_NW")) : 0;
-  P.ng = ng_env > 0 ? ng_env : (P.d <= 64 ? 6 : 4);
-  const uint32_t budget = 232448u - 1024u - 1024u;
-  int na = (int)((budget - (uint32_t)P.ng * g_bytes) / kTileA);
-  if (na > 12) na = 12;
-  if (na < 2) return proj_wgrad_ts_launch(P0, grid, st);
-  P.stages = na;
-  const uint32_t smem = (uint32_t)na * kTileA + (uint32_t)P.ng * g_bytes + 1024 + 1024;
-  cudaFuncSetAttribute(proj_wgrad_ts3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  proj_wgrad_ts3_kernel<<<grid, 512, smem, st>>>(P);
-  LLMREC_CHECK_LAUNCH("proj_wgrad_ts3");
   return 0;
 }
 int proj_wgrad_ts_launch(const WgParams& P0, int grid, cudaStream_t st) {

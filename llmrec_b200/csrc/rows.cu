@@ -51,16 +51,6 @@ __global__ void __launch_bounds__(256) scatter_add_rows_kernel(const float* __re
   if (r < 0) return;
   for (int j = lane; j < d; j += 32) atomicAdd(Y + (int64_t)r * ldy + j, G[(int64_t)b * ldg + j]);
 }
-// Xp[(p*npad + r)*32 + c] = r < n ? X[r*ldx + 32p + c] : 0: one float4 per thread, 128-byte segments on both sides
-__global__ void __launch_bounds__(256) panelize_kernel(const float* __restrict__ X, int64_t ldx, int64_t n, int64_t npad, int panels, float* __restrict__ Xp) {
-  const int64_t total = npad * (int64_t)panels * 8;   // float4 count
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int q = (int)(i & 7);
-    const int64_t row = i >> 3;                       // output row = p*npad + r
-    const int64_t p = row / npad, r = row - p * npad;
-    reinterpret_cast<float4*>(Xp)[i] = r < n ? __ldg(reinterpret_cast<const float4*>(X + r * ldx + p * 32) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-}
 // ---- row sets of the demand-driven training step (dist.py): bitmask over rows, built and compacted on the device -----------------
 // mask |= bit(v) for every v in the CSR rows named by list[0..n_list) -- one CTA per listed row (hub rows have 1e5 entries)
 __global__ void __launch_bounds__(256) mark_neighbors_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const int* __restrict__ list,
@@ -151,19 +141,6 @@ extern "C" int llmrec_assign_rows_f32(const float* G, int64_t ldg, const int32_t
   if (n <= 0) return 0;
   assign_rows_kernel<<<(n + 7) / 8, 256, 0, as_stream(stream)>>>(G, ldg, idx, n, d, Y, ldy);
   LLMREC_CHECK_LAUNCH("assign_rows");
-  return 0;
-}
-
-extern "C" int llmrec_panelize_f32(const float* X, int64_t ldx, int64_t n, int32_t k, float* Xp, llmrec_stream_t stream) {
-  LLMREC_REQUIRE_DEVICE();
-  LLMREC_CHECK_ARG(k >= 32 && k % 32 == 0 && ldx >= k && ldx % 4 == 0 && aligned16(X) && aligned16(Xp), "panelize: k %% 32 == 0, ldx %% 4 == 0 and 16-byte aligned pointers required");
-  if (n <= 0) return 0;
-  const int64_t npad = LLMREC_PANEL_ROWS(n);
-  const int64_t total = npad * (int64_t)(k / 32) * 8;
-  int64_t blocks = (total + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  panelize_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(X, ldx, n, npad, k / 32, Xp);
-  LLMREC_CHECK_LAUNCH("panelize");
   return 0;
 }
 

@@ -609,16 +609,8 @@ extern "C" int llmrec_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, co
     }
     if (p.total_f4 <= 8) rc = launch_spmm<8, 1, 4>(p, st);
     else if (p.total_f4 <= 16) rc = launch_spmm<16, 1, 4>(p, st);
-    else {  // 32 lanes x one 16-byte chunk; wider concatenations run as 32-chunk column windows over blockIdx.y
-      static const int variant = getenv("LLMREC_SPMM_VARIANT") ? atoi(getenv("LLMREC_SPMM_VARIANT")) : 0;
-      switch (variant) {
-        case 1: rc = launch_spmm<32, 1, 8, 3>(p, st); break;   // 8 gathers in flight per lane, 24 warps/SM
-        case 2: rc = launch_spmm<32, 1, 8, 4>(p, st); break;
-        case 3: rc = launch_spmm<32, 1, 4, 6>(p, st); break;   // 48 warps/SM
-        case 4: rc = launch_spmm<32, 1, 2, 8>(p, st); break;   // 64 warps/SM
-        default: rc = launch_spmm<32, 1, 4, 4>(p, st); break;
-      }
-    }
+    else rc = launch_spmm<32, 1, 4, 4>(p, st);  // 32 lanes x one 16-byte chunk, 4 gathers in flight per lane, 32 warps/SM (8 in flight / 48-64 warps per SM
+                                                // measured 15-140 % slower at the synthetic scale); wider concatenations run as 32-chunk column windows over blockIdx.y
     if (rc) return rc;
   }
   return 0;

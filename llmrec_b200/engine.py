@@ -39,7 +39,6 @@ class HotPathConfig:
     batch_size: int = 1024
     aug_sample_rate: float = 0.1      # main.py:218: a batch grows by at most int(batch_size * rate) augmented triplets
     proj_mode: int = 0                # ops.PROJ_MODE
-    feat_layout: int = 0              # 0 = row-major feature tables, 1 = 32-column panels (ops.PanelFeat; tcgen05 modes only)
 
 
 PARAM_ORDER = ("image_trans.weight", "image_trans.bias", "text_trans.weight", "text_trans.bias",
@@ -89,10 +88,6 @@ class HotPath:
         self.keys = list(feats["item"].keys()) if self.has_feats else []
         S = self.S = (2 + len(self.keys)) if self.has_feats else 0
         self.fx = feats                                                    # what the projection kernels read
-        if self.has_feats and cfg.feat_layout == 1 and cfg.proj_mode != 2:
-            pf = lambda t: ops.PanelFeat(t) if t.shape[1] % 32 == 0 else t
-            self.fx = dict(image=pf(feats["image"]), text=pf(feats["text"]), user=pf(feats["user"]),
-                           item={k: pf(v) for k, v in feats["item"].items()})
         if self.has_feats:
             self.Pi, self.Fu, self.Fi = new(ni, S * d), new(nu, S * d), new(ni, S * d)
             self.P_usr, self.prof_i, self.prof_u = new(nu, d), new(ni, d), new(nu, d)

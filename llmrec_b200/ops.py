@@ -210,48 +210,17 @@ def _get_scratch(key, n, device):
     return t
 
 
-class PanelFeat:
-    """A constant feature table X[n x k] re-laid out by llmrec_panelize_f32 (LLMREC_X_PANELS): k/32 column panels, each a
-    contiguous [n_pad x 32] block (n rounded up to 128, zero padded), so the [rows x 32] tiles of the projection kernels
-    are contiguous DRAM runs."""
-
-    def __init__(self, X):
-        _mat(X)
-        n, k = X.shape
-        if k % 32:
-            raise ValueError("panel layout needs k % 32 == 0")
-        self.shape, self.device = (n, k), X.device
-        self.n_pad = (n + 127) // 128 * 128
-        self.data = torch.empty((k // 32) * self.n_pad, 32, dtype=torch.float32, device=X.device)
-        N.check(N.lib().llmrec_panelize_f32(_p(X), _ld(X), n, k, _p(self.data), _stream()), "panelize")
-        _count()
-
-    def rows(self):
-        """back to row-major [n x k] (tests)"""
-        n, k = self.shape
-        return self.data.view(k // 32, self.n_pad, 32)[:, :n].permute(1, 0, 2).reshape(n, k).contiguous()
-
-
-def _x_operand(X):
-    """-> (device tensor, leading dimension, LLMREC_X_ROWS | LLMREC_X_PANELS)"""
-    if isinstance(X, PanelFeat):
-        return X.data, 32, 1
-    _mat(X)
-    return X, _ld(X), 0
-
-
 def proj_fwd_group(problems, d, mode=0):
-    """problems: list of (X[n x k] tensor or PanelFeat, W[d x k], bias[d]|None, out[n x d]).  One grouped launch (tcgen05) --
+    """problems: list of (X[n x k], W[d x k], bias[d]|None, out[n x d]).  One grouped launch (tcgen05) --
     the 8 nn.Linear calls of Models.py:145-150.  Problems sharing W share the hi/lo split buffer."""
     arr = (N.ProjFwdProblem * len(problems))()
     for i, (X, W, b, out) in enumerate(problems):
         _mat(out)
-        n, k = X.shape
-        xt, ldx, layout = _x_operand(X)
+        n, k = _mat(X).shape
         if not W.is_contiguous() or tuple(W.shape) != (d, k) or tuple(out.shape) != (n, d):
             raise ValueError("proj_fwd: bad shapes")
         ws = _get_scratch(("wsplit", W.data_ptr()), 2 * d * k, X.device) if mode == 0 else None
-        arr[i] = N.ProjFwdProblem(_p(xt), _p(W), _p(b), _p(out), _p(ws), ldx, _ld(out), n, k, layout)
+        arr[i] = N.ProjFwdProblem(_p(X), _p(W), _p(b), _p(out), _p(ws), _ld(X), _ld(out), n, k, 0)
     N.check(N.lib().llmrec_proj_fwd_group_f32(arr, len(problems), d, mode, _stream()), "proj_fwd_group")
     _count(1 + len({int(p.W) for p in arr}) if mode == 0 else 1)
 
@@ -267,11 +236,10 @@ def proj_wgrad_group(problems, d, mode=0):
     arr = (N.ProjWgradProblem * len(problems))()
     for i, (X, dY, dW, db, acc) in enumerate(problems):
         _mat(dY)
-        n, k = X.shape
-        xt, ldx, layout = _x_operand(X)
+        n, k = _mat(X).shape
         if not dW.is_contiguous() or tuple(dW.shape) != (d, k) or tuple(dY.shape) != (n, d):
             raise ValueError("proj_wgrad: bad shapes")
-        arr[i] = N.ProjWgradProblem(_p(xt), _p(dY), _p(dW), _p(db), ldx, _ld(dY), n, k, (1 if acc else 0) | (2 if layout else 0))
+        arr[i] = N.ProjWgradProblem(_p(X), _p(dY), _p(dW), _p(db), _ld(X), _ld(dY), n, k, 1 if acc else 0)
     need = int(N.lib().llmrec_proj_wgrad_group_scratch(arr, len(problems), d, mode))
     scratch = _get_scratch(("wgrad", problems[0][0].device.index), need, problems[0][0].device) if need else None
     N.check(N.lib().llmrec_proj_wgrad_group_f32(arr, len(problems), d, mode, _p(scratch), need, _stream()), "proj_wgrad_group")

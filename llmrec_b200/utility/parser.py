@@ -73,7 +73,6 @@ _FLAGS = _reference_flags()
 # B200-side extras (not in the reference; all optional)
 _EXTRA = [
     ("proj_mode", dict(default="3xtf32", choices=["3xtf32", "tf32", "fp32"], help="tensor-core mode of the projection / scoring GEMMs")),
-    ("feat_layout", dict(default="rows", choices=["rows", "panels"], help="HBM layout of the constant side-feature tables: row-major, or 32-column panels (contiguous tiles for the projection kernels)")),
     ("cuda_graph", dict(type=int, default=1, help="replay the training step from a CUDA graph (1) or launch eagerly (0)")),
     ("host_sampler", dict(default="native", choices=["native", "python"], help="bit-identical C sampler or the reference's Python loops")),
     ("hoist_side", dict(type=int, default=0, help="1: precompute the propagation of the constant side features once (ui.X, iu.ui.X) and project only the "

@@ -20,8 +20,6 @@ if which in ("all", "proj"):
     Wu = torch.randn(d, 1536, device=dev) / 39.0
     b = torch.zeros(d, device=dev)
     outs = [torch.empty(n, d, device=dev) for n, _ in dims]
-    if os.environ.get("PANELS"):                       # feature tables in 32-column panels (ops.PanelFeat)
-        Xs = [ops.PanelFeat(X) for X in Xs]
     fw = [(X, (Wu if i == 5 else Ws[X.shape[1]]), b, o) for i, (X, o) in enumerate(zip(Xs, outs))]
     dWs = [torch.empty(d, X.shape[1], device=dev) for X in Xs]
     dbs = [torch.empty(d, device=dev) for _ in Xs]

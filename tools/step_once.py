@@ -16,7 +16,7 @@ ap.add_argument("--hoist", type=int, default=0)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--spans", type=int, default=1)
 a = ap.parse_args()
-ba = argparse.Namespace(proj_mode="3xtf32", feat_layout="rows", host_sampler="native", graph=0)
+ba = argparse.Namespace(proj_mode="3xtf32", host_sampler="native", graph=0)
 tr, gen, args = bench.make_trainer(a.workload, ba, extra=(["--hoist_side", "1"] if a.hoist else []))
 hp = tr.hot
 for _ in range(3):
