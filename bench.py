@@ -490,6 +490,12 @@ def main():
     out = run_reference(a) if a.impl == "reference" else run_ours(a)
     if out is not None and int(os.environ.get("RANK", 0)) == 0:
         print(json.dumps(out), flush=True)
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
 
 
 if __name__ == "__main__":

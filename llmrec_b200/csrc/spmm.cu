@@ -184,15 +184,16 @@ __global__ void __launch_bounds__(256, MINB) spmm_tile_kernel(const SpmmParams p
 // the warp then reads the staged rows conflict-free (lane = 16-byte chunk) and accumulates with the same row-boundary / epilogue logic
 // as the register kernel.  Per SM up to 12 warps x 3 stages x 4 KiB = 144 KiB of gathers are in flight without holding a register,
 // which is what a DRAM-latency-bound random gather wants.  Same tile descriptors, same sums in the same order (bit-identical results).
-constexpr bool kSpmmBulkAuto = false;   // flipped to true once the A/B on the large graph says so (tools/spmm_scale.py, LLMREC_SPMM_BULK=0/1)
-constexpr int kBulkStages = 4;
+constexpr bool kSpmmBulkAuto = true;    // A/B at the synthetic scale (profiles/r2_spmm_ab.txt): 12 % faster than register gathers when the gathered table is far
+                                        // larger than L2 (5.1 GB user table, DRAM-bound), 10 % slower on the 512 MB item table (46 % L2 hits) -> size threshold below
+constexpr int kBulkStages = 3;
 constexpr int kBulkRows = 8;
-constexpr int kBulkWarps = 4;
+constexpr int kBulkWarps = 8;   // 8 warps x 3 stages x 4 KiB = 96 KiB per CTA, 2 CTAs per SM
 __device__ __forceinline__ void bulk_row_load(void* dst, const float* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(tc::smem_u32(dst)), "l"(src), "r"(bytes), "r"(tc::smem_u32(bar)) : "memory");
 }
-__global__ void __launch_bounds__(kBulkWarps * 32, 3) spmm_bulk_kernel(const SpmmParams p) {
+__global__ void __launch_bounds__(kBulkWarps * 32, 2) spmm_bulk_kernel(const SpmmParams p) {
   extern __shared__ __align__(128) uint8_t bulk_smem[];
   constexpr int ROWB = 512;                                        // d = 128 fp32
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -224,9 +225,10 @@ __global__ void __launch_bounds__(kBulkWarps * 32, 3) spmm_bulk_kernel(const Spm
   const float* X = p.seg[0].X;
   const int64_t ldx = p.seg[0].ldx;
   // column / weight stream in 32-entry chunks: chunk c lives in (cidx[c & 1], w[c & 1]); the issue side runs < 32 entries ahead
-  int cidx0 = 0, cidx1 = 0;
-  float wv0 = 0.f, wv1 = 0.f;
-  auto load_chunk = [&](int c) {
+  int cidx0 = 0, cidx1 = 0, cidx2 = 0;
+  float wv0 = 0.f, wv1 = 0.f, wv2 = 0.f;
+  auto load_chunk = [&](int c) {                                   // chunk c -> register slot c % 3; issued ONE chunk ahead of its first use
+    if (c * 32 >= len) return;
     const int e = e0 + c * 32 + lane;
     int ci = 0; float w = 0.f;
     if (e < e1) {
@@ -234,14 +236,18 @@ __global__ void __launch_bounds__(kBulkWarps * 32, 3) spmm_bulk_kernel(const Spm
       w = p.vals ? __ldg(p.vals + e) : 1.0f;
       if (p.cs) w *= __ldg(p.cs + ci);
     }
-    if (c & 1) { cidx1 = ci; wv1 = w; } else { cidx0 = ci; wv0 = w; }
+    const int sl = c % 3;
+    if (sl == 0) { cidx0 = ci; wv0 = w; } else if (sl == 1) { cidx1 = ci; wv1 = w; } else { cidx2 = ci; wv2 = w; }
   };
+  auto cidx_of = [&](int c) { const int sl = c % 3; return sl == 0 ? cidx0 : (sl == 1 ? cidx1 : cidx2); };
+  auto w_of = [&](int c) { const int sl = c % 3; return sl == 0 ? wv0 : (sl == 1 ? wv1 : wv2); };
+  load_chunk(0);
   auto issue = [&](int g) {                                        // stage g % S <- rows of edges [8g, 8g + 8)
-    if ((g & 3) == 0) load_chunk(g >> 2);
+    if ((g & 3) == 0) load_chunk((g >> 2) + 1);                    // prefetch the NEXT chunk: its latency hides behind 4 groups of copies
     const int s = g % kBulkStages;
     const int k0 = g * kBulkRows;
     const int nvalid = min(kBulkRows, len - k0);
-    const int cj = __shfl_sync(0xffffffffu, ((g >> 2) & 1) ? cidx1 : cidx0, (k0 + (lane & 7)) & 31);
+    const int cj = __shfl_sync(0xffffffffu, cidx_of(g >> 2), (k0 + (lane & 7)) & 31);
     if (lane == 0) tc::mbar_arrive_expect_tx(&bars[s], (uint32_t)nvalid * ROWB);
     __syncwarp();
     if (lane < nvalid) bulk_row_load(ring + ((size_t)s * kBulkRows + lane) * ROWB, X + (int64_t)cj * ldx, ROWB, &bars[s]);
@@ -254,7 +260,7 @@ __global__ void __launch_bounds__(kBulkWarps * 32, 3) spmm_bulk_kernel(const Spm
     tc::mbar_wait(&bars[s], (uint32_t)((g / kBulkStages) & 1));
     const int k0 = g * kBulkRows;
     const int nvalid = min(kBulkRows, len - k0);
-    const float wmine = ((g >> 2) & 1) ? wv1 : wv0;
+    const float wmine = w_of(g >> 2);
 #pragma unroll
     for (int j = 0; j < kBulkRows; ++j) {
       if (j < nvalid) {
@@ -598,7 +604,7 @@ extern "C" int llmrec_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, co
     int rc = 0;
     static const int bulk_mode = getenv("LLMREC_SPMM_BULK") ? atoi(getenv("LLMREC_SPMM_BULK")) : -1;   // -1 auto, 0 off, 1 on
     const bool bulk_ok = p.nseg == 1 && d == 128 && !p.src_mask && segs[s0].ldx == 128;
-    if (bulk_ok && (bulk_mode == 1 || (bulk_mode == -1 && kSpmmBulkAuto && (int64_t)n_cols * 512 > ((int64_t)192 << 20)))) {
+    if (bulk_ok && (bulk_mode == 1 || (bulk_mode == -1 && kSpmmBulkAuto && (int64_t)n_cols * 512 >= ((int64_t)576 << 20)))) {
       const size_t smem = (size_t)kBulkWarps * kBulkStages * kBulkRows * 512 + kBulkWarps * kBulkStages * sizeof(uint64_t);
       static bool attr = false;
       if (!attr) { cudaFuncSetAttribute(spmm_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }

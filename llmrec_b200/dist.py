@@ -159,7 +159,7 @@ class ShardedHotPath:
         dist.all_gather_into_tensor(full, full[self.ilo:self.ihi], group=self.group)
         self.comm_bytes += full.numel() * 2
 
-    def _exchange(self, which, src, out=None, src_mask=None):
+    def _exchange(self, which, src, out=None, src_mask=None, overlap=None):
         """self.part = sum over ranks of (item-side operator `which`) . src.  With item-row pieces, the NCCL all-reduce of
         piece k runs on NCCL's stream while the SpMM of piece k+1 runs on the compute stream (NVLink transfer hidden
         behind the gather)."""
@@ -167,13 +167,24 @@ class ShardedHotPath:
         part = self.part if out is None else out
         if self.world == 1 or not g.pieces:
             (g.iu_raw if which == "iu" else g.uiT_raw).apply([(src, part, None, False)], src_mask=src_mask)
-            self._allreduce(part)
+            if overlap is not None and self.world > 1:
+                # the NCCL kernels run on NCCL's stream; independent work queued on the compute stream now overlaps the transfer
+                work = dist.all_reduce(part, group=self.group, async_op=True)
+                self.comm_bytes += part.numel() * 4
+                overlap()
+                work.wait()
+            else:
+                self._allreduce(part)
+                if overlap is not None:
+                    overlap()
             return
         works = []
         for lo, hi, fwd, bwd in g.pieces:
             (fwd if which == "iu" else bwd).apply([(src, part[lo:hi], None, False)], src_mask=src_mask)
             works.append(dist.all_reduce(part[lo:hi], group=self.group, async_op=True))
             self.comm_bytes += (hi - lo) * self.d * 4
+        if overlap is not None:
+            overlap()
         for w in works:
             w.wait()
 
@@ -279,14 +290,17 @@ class ShardedHotPath:
         local = owner_local_index(users, self.lo, self.hi)
         self.pn[:B].copy_(pos); self.pn[B:].copy_(neg)
         pn = self.pn
-        # row sets of this step (device-side, no host sync)
-        self.needU.clear(); self.needU.add_neighbors(g.rowptr_i, g.col_i, pn); self.needU.add_ids(local); self.needU.compact()
-        self.batchU.clear(); self.batchU.add_ids(local)
+        # row sets of this step (device-side, no host sync); built while the first forward exchange is in flight when there is one
+        def build_sets():
+            self.needU.clear(); self.needU.add_neighbors(g.rowptr_i, g.col_i, pn); self.needU.add_ids(local); self.needU.compact()
+            self.batchU.clear(); self.batchU.add_ids(local)
+        if L < 2:
+            build_sets()
         rows, cnt = self.needU.list, self.needU.count
         # ---- forward: layers 1 .. L-1 dense, layer L on the rows the loss can reach ----
         for l in range(1, L):
             g.ui.apply([(self.Il[l - 1], self.Ul[l], None, False)])
-            self._exchange("iu", self.Ul[l])
+            self._exchange("iu", self.Ul[l], overlap=build_sets if l == 1 else None)
             ops.row_scale_softmax(self.part, g.si, self.Il[l], False)
         g.ui.apply_rows((self.Il[L - 1], self.Ul[L], None, True), rows, cnt)                  # U_L = softmax(ui . I_{L-1}) on needU
         g.iu_raw.apply_rows((self.Ul[L], self.part, None, False), pn, self.cnt_pn, cta_per_row=True)   # this rank's partial of R^T U_L on the batch items (hub items: 1e5 neighbours)
@@ -306,6 +320,16 @@ class ShardedHotPath:
         ops.fuse_bwd(self.gUb, L + 1, self.dUb, [], [], [], False)                            # the mean's share of every layer: g / (L+1)
         ops.fuse_bwd(self.gIb, L + 1, self.dIb, [], [], [], False)
         # ---- backward chain ----
+        # E_u enters the step only through the mean over layers (U_0): its gradient is dUb on the batch rows, known now.  The dense AdamW
+        # pass over the user table (row-sparse gradient) is queued while the first backward exchange is in flight.
+        self.opt.advance()
+        done = []
+
+        def update_users():
+            ops.zero_rows(self.g_Eu, local)
+            ops.scatter_add_rows(self.dUb, local, self.g_Eu)
+            self.opt.step_tensor(0, self.g_Eu, row_mask=self.batchU.mask)
+            done.append(1)
         ops.fill(self.dIl, 0.0)
         ops.scatter_add_rows(self.dIb, pn, self.dIl)
         g_cur = self.dIl
@@ -315,7 +339,7 @@ class ShardedHotPath:
                 g.iuT.apply_rows((src, self.bufU, None, False), rows, cnt)                    # gU_L on needU (the only rows src reaches)
                 ops.scatter_add_rows(self.dUb, local, self.bufU)
                 ops.row_softmax_bwd_rows(self.Ul[l], self.bufU, self.bufU, rows, cnt)
-                self._exchange("uiT", self.bufU, out=self.parts[l & 1], src_mask=self.needU.mask)
+                self._exchange("uiT", self.bufU, out=self.parts[l & 1], src_mask=self.needU.mask, overlap=update_users)
             else:
                 g.iuT.apply([(g_cur, self.bufU, None, False)])
                 ops.scatter_add_rows(self.dUb, local, self.bufU)
@@ -323,9 +347,9 @@ class ShardedHotPath:
             g_cur = self.parts[l & 1]
             ops.scatter_add_rows(self.dIb, pn, g_cur)                                         # + dI_{l-1} (row-sparse addend)
         self.g_Ei = g_cur
-        ops.zero_rows(self.g_Eu, local)                                                       # grad of E_u: the batch rows only
-        ops.scatter_add_rows(self.dUb, local, self.g_Eu)
-        self.opt.step([self.g_Eu, self.g_Ei], row_masks=[self.batchU.mask, None])
+        if not done:
+            update_users()
+        self.opt.step_tensor(1, self.g_Ei)
         return self.loss
 
     def train_step(self, users, pos, neg):

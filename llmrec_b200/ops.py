@@ -358,6 +358,24 @@ class AdamW:
         self.state = torch.zeros(4, dtype=torch.float64, device=dev)
         self._n = (C.c_int64 * len(self.params))(*[p.numel() for p in self.params])
 
+    def advance(self):
+        """bump the device-side step counter / bias corrections once per optimizer step (before any step_tensor)"""
+        N.check(N.lib().llmrec_adamw_advance(_p(self.state), self.lr, self.betas[0], self.betas[1], _stream()), "adamw_advance")
+        _count()
+
+    def step_tensor(self, i, grad, row_mask=None):
+        """update parameter i alone (after advance()): lets independent tables be updated at different points of a step, e.g. the
+        user table while an item-side exchange is in flight"""
+        lib, p = N.lib(), self.params[i]
+        if row_mask is not None:
+            N.check(lib.llmrec_adamw_step_rows_f32(_p(p), _p(grad), _p(self.m[i]), _p(self.v[i]), p.shape[0], p.shape[1], _p(row_mask), _p(self.state),
+                                                    self.lr, self.betas[0], self.betas[1], self.eps, self.wd, _stream()), "adamw_step_rows")
+        else:
+            n = (C.c_int64 * 1)(p.numel())
+            N.check(lib.llmrec_adamw_step_f32(_ptr_table([p.data]), _ptr_table([grad]), _ptr_table([self.m[i]]), _ptr_table([self.v[i]]), n, 1, _p(self.state),
+                                               self.lr, self.betas[0], self.betas[1], self.eps, self.wd, _stream()), "adamw_step")
+        _count()
+
     def step(self, grads, row_masks=None):
         """row_masks: optional list (one entry per parameter) of RowSet-style bitmasks or None: a masked [n x w] parameter reads its
         gradient only on the flagged rows and takes the g = 0 update elsewhere (row-sparse gradients of a dense AdamW)."""

@@ -273,6 +273,22 @@ class AdamW:                                             # llmrec_adamw_advance 
         self.v = [torch.zeros_like(p) for p in self.params]
         self.t = 0
 
+    def advance(self):
+        self.t += 1
+
+    def step_tensor(self, i, grad, row_mask=None):
+        if row_mask is not None:
+            grad = torch.where(_bits(row_mask, grad.shape[0])[:, None], grad, torch.zeros_like(grad))
+        self._update(self.params[i], grad, self.m[i], self.v[i])
+
+    def _update(self, p, g, m, v):
+        b1, b2 = self.betas
+        p.mul_(1 - self.lr * self.wd)
+        m.mul_(b1).add_(g, alpha=1 - b1)
+        v.mul_(b2).addcmul_(g, g, value=1 - b2)
+        denom = (v.sqrt() / (1 - b2 ** self.t) ** 0.5).add_(self.eps)
+        p.addcdiv_(m, denom, value=-self.lr / (1 - b1 ** self.t))
+
     def step(self, grads, row_masks=None):
         self.t += 1
         b1, b2 = self.betas
