@@ -133,6 +133,7 @@ class ShardedHotPath:
         else:
             self.opt = ops.AdamW([E_u_local, E_i], lr=1e-4)
         self.comm_bytes = 0
+        self.item_opt_sharded = False
         # demand-driven training step: the LAST propagation layer reaches the loss only through the batch (U_L on the batch users and
         # on the neighbours of the batch items, I_L on the batch items), so its four products are evaluated on those rows only and the
         # user table's gradient stays row-sparse; every value that is computed is the same sum as in the dense schedule.
@@ -140,6 +141,15 @@ class ShardedHotPath:
         if self.demand:
             self.needU = ops.RowSet(nu, dev)        # local users whose U_L row this step reads
             self.batchU = ops.RowSet(nu, dev)       # local batch users (rows of the user table that receive a gradient)
+            # the LAST exchange of a step yields the gradient of E_i, which only its AdamW update reads: reduce-scatter it, update this rank's
+            # 1/G of the item rows (moments sharded too), all-gather the updated rows -- the bytes of the all-reduce, 1/G of the optimizer work
+            self.item_opt_sharded = self.world > 1 and ni % self.world == 0
+            if self.item_opt_sharded:
+                rank = dist.get_rank(group)
+                per = ni // self.world
+                self.ilo, self.ihi = rank * per, (rank + 1) * per
+                self.shard = new(per, d)
+                self.opt = ops.AdamW([E_u_local, E_i[self.ilo:self.ihi]], lr=1e-4)
 
     def set_lr(self, lr):
         self.opt.lr = lr
@@ -339,10 +349,29 @@ class ShardedHotPath:
                 g.iuT.apply_rows((src, self.bufU, None, False), rows, cnt)                    # gU_L on needU (the only rows src reaches)
                 ops.scatter_add_rows(self.dUb, local, self.bufU)
                 ops.row_softmax_bwd_rows(self.Ul[l], self.bufU, self.bufU, rows, cnt)
-                self._exchange("uiT", self.bufU, out=self.parts[l & 1], src_mask=self.needU.mask, overlap=update_users)
+                mask = self.needU.mask
             else:
                 g.iuT.apply([(g_cur, self.bufU, None, False)])
                 ops.scatter_add_rows(self.dUb, local, self.bufU)
+                mask = None
+            if l == 1 and self.item_opt_sharded:
+                g.uiT_raw.apply([(self.bufU, self.parts[1], None, False)], src_mask=mask)      # this rank's partial of the gradient of E_i
+                work = dist.reduce_scatter_tensor(self.shard, self.parts[1], group=self.group, async_op=True)
+                self.comm_bytes += self.parts[1].numel() * 2
+                if not done:
+                    update_users()                                                            # overlaps the transfer
+                pn64 = pn.to(torch.int64)
+                own = (pn64 >= self.ilo) & (pn64 < self.ihi)
+                idx = torch.where(own, pn64 - self.ilo, torch.full_like(pn64, -1)).to(torch.int32)
+                work.wait()
+                ops.scatter_add_rows(self.dIb, idx, self.shard)                               # + dI_0 on this rank's rows
+                self.g_Ei = self.shard
+                self.opt.step_tensor(1, self.shard)
+                self._all_gather_rows(self.E_i)                                               # updated item rows back to every rank
+                return self.loss
+            if l == L:
+                self._exchange("uiT", self.bufU, out=self.parts[l & 1], src_mask=mask, overlap=update_users)
+            else:
                 self._exchange("uiT", self.bufU, out=self.parts[l & 1])
             g_cur = self.parts[l & 1]
             ops.scatter_add_rows(self.dIb, pn, g_cur)                                         # + dI_{l-1} (row-sparse addend)

@@ -315,11 +315,16 @@ def install():
     D.CsrOperator = CsrOperator
     G.CsrOperator = CsrOperator
 
-    def reduce_scatter_tensor(out, inp, group=None):
+    class _Done:
+        def wait(self):
+            return True
+
+    def reduce_scatter_tensor(out, inp, group=None, async_op=False):
         t = inp.clone()
         dist.all_reduce(t, group=group)
         r, n = dist.get_rank(group), out.shape[0]
         out.copy_(t[r * n:(r + 1) * n])
+        return _Done() if async_op else None
 
     def all_gather_into_tensor(out, inp, group=None):
         parts = [torch.empty_like(inp) for _ in range(dist.get_world_size(group))]
