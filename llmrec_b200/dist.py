@@ -141,6 +141,7 @@ class ShardedHotPath:
         if self.demand:
             self.needU = ops.RowSet(nu, dev)        # local users whose U_L row this step reads
             self.batchU = ops.RowSet(nu, dev)       # local batch users (rows of the user table that receive a gradient)
+            self.batchI = ops.RowSet(ni, dev)       # batch items (the only non-zero rows of the top-layer item gradient)
             # the LAST exchange of a step yields the gradient of E_i, which only its AdamW update reads: reduce-scatter it, update this rank's
             # 1/G of the item rows (moments sharded too), all-gather the updated rows -- the bytes of the all-reduce, 1/G of the optimizer work
             self.item_opt_sharded = self.world > 1 and ni % self.world == 0
@@ -304,6 +305,7 @@ class ShardedHotPath:
         def build_sets():
             self.needU.clear(); self.needU.add_neighbors(g.rowptr_i, g.col_i, pn); self.needU.add_ids(local); self.needU.compact()
             self.batchU.clear(); self.batchU.add_ids(local)
+            self.batchI.clear(); self.batchI.add_ids(pn)
         if L < 2:
             build_sets()
         rows, cnt = self.needU.list, self.needU.count
@@ -340,13 +342,15 @@ class ShardedHotPath:
             ops.scatter_add_rows(self.dUb, local, self.g_Eu)
             self.opt.step_tensor(0, self.g_Eu, row_mask=self.batchU.mask)
             done.append(1)
-        ops.fill(self.dIl, 0.0)
-        ops.scatter_add_rows(self.dIb, pn, self.dIl)
-        g_cur = self.dIl
+        g_cur = None
         for l in range(L, 0, -1):
             if l == L:
-                src = ops.row_softmax_bwd(self.Il[l], g_cur, out=self.tmpI)                   # zero outside the batch items
-                g.iuT.apply_rows((src, self.bufU, None, False), rows, cnt)                    # gU_L on needU (the only rows src reaches)
+                # the top-layer item gradient lives on the batch items only: softmax backward per batch position on the compact rows
+                # (linear in the gradient, so duplicates add up), scattered into the rows of tmpI the source mask lets the gather read
+                ops.row_softmax_bwd(self.Pc, self.dIb, out=self.Ib)                           # Pc still holds I_L on the batch rows; Ib is free now
+                ops.zero_rows(self.tmpI, pn)
+                ops.scatter_add_rows(self.Ib, pn, self.tmpI)
+                g.iuT.apply_rows((self.tmpI, self.bufU, None, False), rows, cnt, src_mask=self.batchI.mask)   # gU_L on needU (the only rows it reaches)
                 ops.scatter_add_rows(self.dUb, local, self.bufU)
                 ops.row_softmax_bwd_rows(self.Ul[l], self.bufU, self.bufU, rows, cnt)
                 mask = self.needU.mask

@@ -86,7 +86,7 @@ def _worker(rank, world, port, item_sharded, pieces, out, demand=False):
     if demand:                                           # rows the demand mode never writes must not leak into results: poison them
         for t in sh.Ul[1:] + sh.Il[1:]:
             t.fill_(123.0)
-        sh.g_Eu.fill_(float("nan")); sh.bufU.fill_(float("nan"))
+        sh.g_Eu.fill_(float("nan")); sh.bufU.fill_(float("nan")); sh.tmpI.fill_(float("nan"))
     sh.set_lr(LR)
     tol = dict(rtol=2e-4, atol=2e-6)
     ok = True
