@@ -287,7 +287,7 @@ class ShardedHotPath:
         new = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
         self.Ub, self.gUb, self.dUb = new(B, d), new(B, d), new(B, d)
         self.Ib, self.gIb, self.dIb = new(2 * B, d), new(2 * B, d), new(2 * B, d)
-        self.Pc, self.sic = new(2 * B, d), new(2 * B, 1)
+        self.Pc, self.sic, self.srcI = new(2 * B, d), new(2 * B, 1), new(2 * B, d)
         self.arange = torch.arange(B, dtype=torch.int32, device=dev)
         self.arange2 = self.arange + B
         self.pn = torch.empty(2 * B, dtype=torch.int32, device=dev)
@@ -347,9 +347,9 @@ class ShardedHotPath:
             if l == L:
                 # the top-layer item gradient lives on the batch items only: softmax backward per batch position on the compact rows
                 # (linear in the gradient, so duplicates add up), scattered into the rows of tmpI the source mask lets the gather read
-                ops.row_softmax_bwd(self.Pc, self.dIb, out=self.Ib)                           # Pc still holds I_L on the batch rows; Ib is free now
+                ops.row_softmax_bwd(self.Pc, self.dIb, out=self.srcI)                         # Pc still holds I_L on the batch rows
                 ops.zero_rows(self.tmpI, pn)
-                ops.scatter_add_rows(self.Ib, pn, self.tmpI)
+                ops.scatter_add_rows(self.srcI, pn, self.tmpI)
                 g.iuT.apply_rows((self.tmpI, self.bufU, None, False), rows, cnt, src_mask=self.batchI.mask)   # gU_L on needU (the only rows it reaches)
                 ops.scatter_add_rows(self.dUb, local, self.bufU)
                 ops.row_softmax_bwd_rows(self.Ul[l], self.bufU, self.bufU, rows, cnt)
