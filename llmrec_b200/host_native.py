@@ -86,13 +86,22 @@ class BatchSampler:
         self.aug_neg = None if aug_neg is None else np.ascontiguousarray(aug_neg, dtype=np.int32)
 
     @staticmethod
-    def aug_tables(aug_dict, n_users):
-        """{uid: {0: pos, 1: neg}} (main.py:216-220) -> two int32[n_users] tables."""
+    def aug_tables(aug_dict, n_users, n_items=None):
+        """{uid: {0: pos, 1: neg}} (main.py:216-220) -> two int32[n_users] tables.
+        Upstream a NEGATIVE id passes the `< n_items` filter (main.py:219-221) and then wraps around under Python / torch negative
+        indexing (row -1 = the last item).  The kernels take row ids literally, so with n_items given the wrap is applied here, once;
+        ids below -n_items (an IndexError upstream) are marked missing."""
         pos = np.full(n_users, BatchSampler.MISSING, dtype=np.int32)
         neg = np.full(n_users, BatchSampler.MISSING, dtype=np.int32)
+
+        def wrap(i):
+            i = int(i)
+            if i < 0 and n_items is not None:
+                return i + n_items if i >= -n_items else BatchSampler.MISSING
+            return i
         for u, pn in aug_dict.items():
             if 0 <= u < n_users:
-                pos[u], neg[u] = pn[0], pn[1]
+                pos[u], neg[u] = wrap(pn[0]), wrap(pn[1])
         return pos, neg
 
     def draw(self, out, aug_rate=0.0):

@@ -130,7 +130,7 @@ class Trainer(object):
         if getattr(data_generator, "_sampler", "python") == "native":
             from .host_native import BatchSampler
             rowptr, col = data_generator.csr("train")
-            aug_pos, aug_neg = BatchSampler.aug_tables(self.augmented_sample_dict, data_generator.n_users)
+            aug_pos, aug_neg = BatchSampler.aug_tables(self.augmented_sample_dict, data_generator.n_users, self.n_items)
             self._batch_sampler = BatchSampler(data_generator.exist_users, rowptr, col, data_generator.n_items, data_generator.batch_size,
                                                aug_pos, aug_neg, aug_limit=self.n_items)
             self._batch_np = np.empty((3, 2 * data_generator.batch_size + 8), dtype=np.int32)
@@ -142,7 +142,7 @@ class Trainer(object):
             from .device_sampler import DeviceSampler
             from .host_native import BatchSampler
             rowptr, col = data_generator.csr("train", sorted_rows=True)
-            aug_pos, aug_neg = BatchSampler.aug_tables(self.augmented_sample_dict, data_generator.n_users)
+            aug_pos, aug_neg = BatchSampler.aug_tables(self.augmented_sample_dict, data_generator.n_users, self.n_items)
             self.device_sampler = DeviceSampler(data_generator.exist_users, rowptr, col, data_generator.n_items, data_generator.batch_size,
                                                 aug_pos, aug_neg, self.n_items, args.aug_sample_rate, self.device, seed=args.seed)
             gi = self.hot.index_buffer(self.hot.batch_capacity())
@@ -291,8 +291,9 @@ class Trainer(object):
         keep = [u for u in users_aug if (aug[u][0] < ni and aug[u][1] < ni)]
         self.new_batch_size = len(keep)
         users = users + keep
-        pos_items = pos_items + [aug[u][0] for u in keep]
-        neg_items = neg_items + [aug[u][1] for u in keep]
+        # a negative augmented id passes upstream's filter and wraps under Python indexing (row -1 = last item): same row here
+        pos_items = pos_items + [aug[u][0] % ni for u in keep]
+        neg_items = neg_items + [aug[u][1] % ni for u in keep]
         return users, pos_items, neg_items
 
     def _next_slot(self, need):

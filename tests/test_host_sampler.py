@@ -106,3 +106,14 @@ def test_batch_sampler_missing_aug_user_raises(tiny_root):
     bs = BatchSampler(gen.exist_users, rp, col, gen.n_items, 128, *BatchSampler.aug_tables({}, gen.n_users))
     with pytest.raises(KeyError):
         bs.draw(np.zeros((3, 300), dtype=np.int32), 0.1)
+
+
+def test_negative_augmented_ids_wrap_like_python_indexing():
+    """upstream a negative augmented id passes the `< n_items` filter (main.py:219-221) and indexes from the end; the kernels take
+    row ids literally, so the tables (and the Python sampling path) apply the wrap once; ids below -n_items are marked missing."""
+    from llmrec_b200.host_native import BatchSampler
+    aug = {0: {0: 5, 1: -1}, 1: {0: -7, 1: 3}, 2: {0: -100, 1: 2}}
+    pos, neg = BatchSampler.aug_tables(aug, 3, n_items=10)
+    assert pos.tolist() == [5, 3, BatchSampler.MISSING] and neg.tolist() == [9, 3, 2]
+    pos, neg = BatchSampler.aug_tables(aug, 3)                      # without n_items the raw values are kept (reference-stream tests)
+    assert pos.tolist() == [5, -7, -100] and neg.tolist() == [-1, 3, 2]
