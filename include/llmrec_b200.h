@@ -61,12 +61,14 @@ typedef struct {
 
 typedef struct {
   const int32_t* tiles;       /* [n_tiles][8] = {first row, #complete rows (0 = one piece of a long row), e0, e1} followed by
-                                 16 one-byte row-end offsets relative to e0; 32-byte aligned; pieces of long rows are
-                                 numbered first (llmrec_spmm_plan_tiles builds this) */
+                                 16 one-byte row-end offsets relative to e0 (pieces: {split index, first piece, #pieces, 0} instead);
+                                 32-byte aligned; pieces of long rows are numbered first (llmrec_spmm_plan_tiles builds this) */
   const int32_t* split_row;   /* [n_split] rows that were cut into pieces */
   const int32_t* split_first; /* [n_split+1] first piece (tile id) of each split row */
   float* scratch;             /* [n_split_tiles * min(nseg,16) * d] partial sums of the pieces */
   int32_t n_tiles, n_split, n_split_tiles, _pad;
+  int32_t* split_tickets;     /* optional int32[n_split * 64], zeroed once: with it the LAST piece of a long row to finish adds the row's
+                                 pieces (in piece order) and runs the epilogue inside the same launch; NULL = second-pass kernel */
   const uint32_t* src_mask;   /* optional bitmask over SOURCE rows (= pattern columns): a clear bit promises that row of X is all zero;
                                  its fetch is skipped (identical sums).  NULL = every row is live. */
 } llmrec_spmm_tiling;
@@ -142,7 +144,8 @@ typedef struct {
 int llmrec_proj_fwd_group_f32(const llmrec_proj_fwd_problem* probs_host, int32_t n_prob, int32_t d, int32_t mode,
                               llmrec_stream_t stream);
 int llmrec_proj_wgrad_group_f32(const llmrec_proj_wgrad_problem* probs_host, int32_t n_prob, int32_t d, int32_t mode,
-                                float* scratch, int64_t scratch_elems, llmrec_stream_t stream);
+                                float* scratch /* zero-initialised ONCE by the caller: its last words are a ticket the kernels leave at zero */,
+                                int64_t scratch_elems, llmrec_stream_t stream);
 int64_t llmrec_proj_wgrad_group_scratch(const llmrec_proj_wgrad_problem* probs_host, int32_t n_prob, int32_t d, int32_t mode);
 
 /* ---------------------------------------------------------------------------------------------

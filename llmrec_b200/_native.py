@@ -25,7 +25,8 @@ class SpmmSeg(C.Structure):
 
 class SpmmTiling(C.Structure):
     _fields_ = [("tiles", C.c_void_p), ("split_row", C.c_void_p), ("split_first", C.c_void_p), ("scratch", C.c_void_p),
-                ("n_tiles", C.c_int32), ("n_split", C.c_int32), ("n_split_tiles", C.c_int32), ("_pad", C.c_int32), ("src_mask", C.c_void_p)]
+                ("n_tiles", C.c_int32), ("n_split", C.c_int32), ("n_split_tiles", C.c_int32), ("_pad", C.c_int32), ("split_tickets", C.c_void_p),
+                ("src_mask", C.c_void_p)]
 
 
 class ProjFwdProblem(C.Structure):

@@ -253,10 +253,15 @@ __global__ void __launch_bounds__(384, 1) proj_fwd_tc_kernel(const __grid_consta
   if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols); }
 }
 
-// W -> [hi ; lo]  ([2d x k], hi exactly TF32-representable)
-__global__ void wsplit_kernel(const float* __restrict__ W, float* __restrict__ out, int64_t n) {
-  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i < n) { float v = W[i]; float h = tf32_hi(v); out[i] = h; out[n + i] = v - h; }
+// W -> [hi ; lo]  ([2d x k], hi exactly TF32-representable); every distinct weight matrix of a grouped launch in ONE launch (blockIdx.y)
+struct WsplitParams { const float* W[kMaxProb]; float* out[kMaxProb]; long long n[kMaxProb]; };
+__global__ void wsplit_kernel(const WsplitParams P) {
+  const float* __restrict__ W = P.W[blockIdx.y];
+  float* __restrict__ out = P.out[blockIdx.y];
+  const long long n = P.n[blockIdx.y];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = W[i]; const float h = tf32_hi(v); out[i] = h; out[n + i] = v - h;
+  }
 }
 
 static uint32_t pow2_cols(int c) { uint32_t r = 32; while ((int)r < c) r <<= 1; return r; }
@@ -445,12 +450,13 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const ReduceParams R)
   }
 }
 
-// db[dc] (+)= sum_r dY[r][dc] : 16 row-slices per problem -> partial, then an ordered combine (deterministic;
-// problems sharing one db -- the 5 attribute matrices behind item_trans -- accumulate in problem order)
-struct ColsumParams { const float* dY[kMaxProb]; long long ld[kMaxProb]; long long n[kMaxProb]; float* db[kMaxProb]; int acc[kMaxProb]; int d; int n_prob; float* partial; };
+// db[dc] (+)= sum_r dY[r][dc] : kColsumSlices row-slices per problem -> partial; the LAST block to finish (ticket) combines them in a fixed
+// order (deterministic; problems sharing one db -- the 5 attribute matrices behind item_trans -- accumulate in problem order).  One launch.
+struct ColsumParams { const float* dY[kMaxProb]; long long ld[kMaxProb]; long long n[kMaxProb]; float* db[kMaxProb]; int acc[kMaxProb]; int d; int n_prob; float* partial; unsigned* ticket; };
 constexpr int kColsumSlices = 128;
-__global__ void __launch_bounds__(256) colsum_partial_kernel(const ColsumParams P) {
+__global__ void __launch_bounds__(256) colsum_kernel(const ColsumParams P) {
   __shared__ float red[256];
+  __shared__ bool s_last;
   const int p = blockIdx.y, b = blockIdx.x, d = P.d;
   const int groups = 256 / d > 0 ? 256 / d : 1;  // d <= 256
   const int g = threadIdx.x / d, c = threadIdx.x - g * d;
@@ -466,28 +472,28 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const ColsumParams 
     for (int gg = 0; gg < groups; ++gg) t += red[gg * d + threadIdx.x];
     P.partial[((long long)p * kColsumSlices + b) * d + threadIdx.x] = t;
   }
-}
-// one block per problem group is not possible (problems sharing db must be combined in order), so: one block, d columns x
-// (1024/d) slice-groups; each thread sums its slices for every problem, fixed-order combine, problems applied in order
-__global__ void __launch_bounds__(1024) colsum_final_kernel(const ColsumParams P) {
-  __shared__ float red[1024];
-  const int d = P.d, groups = 1024 / d;
-  const int g = threadIdx.x / d, c = threadIdx.x - g * d;
-  for (int p = 0; p < P.n_prob; ++p) {
-    if (!P.db[p]) continue;   // uniform
-    float s = 0.f;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(P.ticket, 1u) == gridDim.x * gridDim.y - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int q = 0; q < P.n_prob; ++q) {          // problems in order: shared db accumulate deterministically
+    if (!P.db[q]) continue;                     // uniform
+    float t = 0.f;
     if (g < groups)
-      for (int b = g; b < kColsumSlices; b += groups) s += P.partial[((long long)p * kColsumSlices + b) * d + c];
-    red[threadIdx.x] = (g < groups) ? s : 0.f;
+      for (int bb = g; bb < kColsumSlices; bb += groups) t += __ldcg(P.partial + ((long long)q * kColsumSlices + bb) * d + c);
+    __syncthreads();
+    red[threadIdx.x] = (g < groups) ? t : 0.f;
     __syncthreads();
     if (threadIdx.x < d) {
-      float t = 0.f;
-      for (int gg = 0; gg < groups; ++gg) t += red[gg * d + threadIdx.x];
-      float* o = P.db[p] + threadIdx.x;
-      *o = P.acc[p] ? (*o + t) : t;
+      float u = 0.f;
+      for (int gg = 0; gg < groups; ++gg) u += red[gg * d + threadIdx.x];
+      float* o = P.db[q] + threadIdx.x;
+      *o = P.acc[q] ? (*o + u) : u;
     }
-    __syncthreads();
   }
+  if (threadIdx.x == 0) *P.ticket = 0u;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -512,15 +518,19 @@ int proj_fwd_tc_group(const llmrec_proj_fwd_problem* pr, int n_prob, int d, int 
   memset(&P, 0, sizeof(P));
   P.n_prob = n_prob; P.d = d;
   int tiles = 0;
+  WsplitParams WS;
+  memset(&WS, 0, sizeof(WS));
+  int n_ws = 0;
+  long long ws_max = 0;
   for (int p = 0; p < n_prob; ++p) {
     const float* wsrc = split ? pr[p].wsplit : pr[p].W;
     LLMREC_CHECK_ARG(!split || pr[p].wsplit, "proj_fwd: 3xTF32 mode needs a wsplit buffer of 2*d*k floats");
     bool fresh = true;
     for (int q = 0; q < p; ++q) fresh = fresh && !(pr[q].W == pr[p].W && pr[q].wsplit == pr[p].wsplit);
     if (split && fresh) {
-      int64_t n = (int64_t)d * pr[p].k;
-      wsplit_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pr[p].W, pr[p].wsplit, n);
-      LLMREC_CHECK_LAUNCH("wsplit");
+      WS.W[n_ws] = pr[p].W; WS.out[n_ws] = pr[p].wsplit; WS.n[n_ws] = (long long)d * pr[p].k;
+      ws_max = WS.n[n_ws] > ws_max ? WS.n[n_ws] : ws_max;
+      ++n_ws;
     }
     if (!make_tmap_2d_f32(&P.tmA[p], pr[p].X, (uint64_t)pr[p].k, (uint64_t)pr[p].n, (uint64_t)pr[p].ldx * 4, BK, BM)) return 4;
     if (!make_tmap_2d_f32(&P.tmW[p], wsrc, (uint64_t)pr[p].k, (uint64_t)(split ? 2 * d : d), (uint64_t)pr[p].k * 4, BK, (uint32_t)d)) return 4;
@@ -529,6 +539,10 @@ int proj_fwd_tc_group(const llmrec_proj_fwd_problem* pr, int n_prob, int d, int 
     tiles += (int)((pr[p].n + BM - 1) / BM);
   }
   P.total_tiles = tiles;
+  if (n_ws > 0) {
+    wsplit_kernel<<<dim3((unsigned)((ws_max + 255) / 256), n_ws), 256, 0, st>>>(WS);
+    LLMREC_CHECK_LAUNCH("wsplit");
+  }
   static const int dbg = getenv("LLMREC_PROJ_DBG") ? atoi(getenv("LLMREC_PROJ_DBG")) : 0;   // TIMING experiments (wrong results): 1 no W loads, 2 no MMAs, 4 no transform
   P.dbg = dbg;
   uint32_t smem;
@@ -561,7 +575,7 @@ int64_t proj_wgrad_tc_scratch(const llmrec_proj_wgrad_problem* pr, int n_prob, i
     int rpc = wg_rows_per_chunk(pr[p].n);
     items += (int64_t)((pr[p].k + BM - 1) / BM) * ((pr[p].n + rpc - 1) / rpc);
   }
-  return items * BM * d + (int64_t)n_prob * kColsumSlices * d;
+  return items * BM * d + (int64_t)n_prob * kColsumSlices * d + 4;   // + the colsum ticket (must start at zero; the kernel re-zeroes it)
 }
 
 int proj_wgrad_tc_group(const llmrec_proj_wgrad_problem* pr, int n_prob, int d, int mode, float* scratch, int64_t scratch_elems, cudaStream_t st) {
@@ -585,10 +599,11 @@ int proj_wgrad_tc_group(const llmrec_proj_wgrad_problem* pr, int n_prob, int d, 
     C.dY[p] = pr[p].dY; C.ld[p] = pr[p].lddy; C.n[p] = pr[p].n; C.db[p] = pr[p].db; C.acc[p] = pr[p].accumulate & LLMREC_WGRAD_ACCUMULATE;
   }
   P.total_items = items;
-  const int64_t need = (int64_t)items * BM * d + (int64_t)n_prob * kColsumSlices * d;
+  const int64_t need = (int64_t)items * BM * d + (int64_t)n_prob * kColsumSlices * d + 4;
   LLMREC_CHECK_ARG(scratch && scratch_elems >= need, "proj_wgrad: scratch too small (%lld < %lld)", (long long)scratch_elems, (long long)need);
   P.partial = scratch;
   C.n_prob = n_prob; C.partial = scratch + (int64_t)items * BM * d;
+  C.ticket = reinterpret_cast<unsigned*>(scratch + need - 4);
   uint32_t smem;
   P.stages = stages_for(d, split, &smem);
   P.tmem_cols = (int)pow2_cols(2 * d);
@@ -625,10 +640,12 @@ int proj_wgrad_tc_group(const llmrec_proj_wgrad_problem* pr, int n_prob, int d, 
   for (int o = 0; o < R.n_out; ++o) { R.out[o].blk_start = blocks; blocks += ((R.out[o].k + BM - 1) / BM) * (BM / feats_per_blk); }
   wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(R);
   LLMREC_CHECK_LAUNCH("wgrad_reduce");
-  colsum_partial_kernel<<<dim3(kColsumSlices, n_prob), 256, 0, st>>>(C);
-  LLMREC_CHECK_LAUNCH("colsum_partial");
-  colsum_final_kernel<<<1, 1024, 0, st>>>(C);
-  LLMREC_CHECK_LAUNCH("colsum_final");
+  bool any_db = false;
+  for (int p = 0; p < n_prob; ++p) any_db = any_db || pr[p].db != nullptr;
+  if (any_db) {
+    colsum_kernel<<<dim3(kColsumSlices, n_prob), 256, 0, st>>>(C);
+    LLMREC_CHECK_LAUNCH("colsum");
+  }
   return 0;
 }
 

@@ -24,11 +24,13 @@
 
 namespace llmrec {
 
+constexpr int kTicketWindows = 64;   // column windows (blockIdx.y) a launch can have: 16 segments x 128 floats / 32 lanes
 struct SpmmParams {
   const int* rowptr; const int* col; const float* vals; const float* rs; const float* cs;
   int n_rows; int d; int nseg; int f4_per_seg; int total_f4; int any_softmax;
   const int4* tiles; int n_tiles; int n_split_tiles; float* scratch;
   const int* split_row; const int* split_first; int n_split;
+  int* split_tickets;         // optional int32[n_split * kTicketWindows]: the LAST piece of a long row to finish adds the pieces up (no second launch)
   const unsigned* src_mask;   // optional bitmask over SOURCE rows (columns of the pattern): clear bit = row known to be zero, never fetched
   const int* rows; const int* n_rows_dev; int max_rows;   // row-list form (spmm_rows_kernel)
   llmrec_spmm_seg seg[LLMREC_MAX_SEG];
@@ -172,6 +174,34 @@ __global__ void __launch_bounds__(256, MINB) spmm_tile_kernel(const SpmmParams p
     for (int c = 0; c < CH; ++c) {
       const int q = blockIdx.y * (LPR * CH) + c * LPR + lane_in;
       if (q < p.total_f4) st4(p.scratch + ((int64_t)tile * p.total_f4 + q) * 4, acc[c]);
+    }
+    if (p.split_tickets) {
+      // the descriptor's spare words carry {split index, first piece, #pieces}: whoever finishes LAST adds the pieces in piece order
+      // (the same order as the second-pass kernel: bit-identical sums) and runs the row epilogue -- no spmm_finish launch
+      const int sidx = (int)dl.x, first = (int)dl.y, npieces = (int)dl.z;
+      __threadfence();
+      __syncwarp(gmask);
+      int ticket = 0;
+      int* cnt = p.split_tickets + (size_t)sidx * kTicketWindows + blockIdx.y;
+      if (lane_in == 0) ticket = atomicAdd(cnt, 1);
+      ticket = __shfl_sync(gmask, ticket, 0, LPR);
+      if (ticket == npieces - 1) {
+        __threadfence();
+#pragma unroll
+        for (int c = 0; c < CH; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int t2 = first; t2 < first + npieces; ++t2) {
+#pragma unroll
+          for (int c = 0; c < CH; ++c) {
+            const int q = blockIdx.y * (LPR * CH) + c * LPR + lane_in;
+            if (q < p.total_f4) {
+              const float4 v = __ldcg(reinterpret_cast<const float4*>(p.scratch + ((int64_t)t2 * p.total_f4 + q) * 4));
+              acc[c].x += v.x; acc[c].y += v.y; acc[c].z += v.z; acc[c].w += v.w;
+            }
+          }
+        }
+        finish_row<CH>(p, lc, acc, row0, gmask);
+        if (lane_in == 0) *cnt = 0;
+      }
     }
   } else {
     for (; cur < nrows; ++cur) finish_row<CH>(p, lc, acc, row0 + cur, gmask);  // last row and trailing empty rows
@@ -490,7 +520,7 @@ static int launch_spmm(const SpmmParams& p, cudaStream_t st) {
   const int windows = (p.total_f4 + LPR * CH - 1) / (LPR * CH);
   if (blocks > 0) spmm_tile_kernel<LPR, CH, U, MINB><<<dim3(blocks, windows), 256, 0, st>>>(p);
   LLMREC_CHECK_LAUNCH("spmm_tile");
-  if (p.n_split > 0) {
+  if (p.n_split > 0 && !p.split_tickets) {
     const int fw = (p.total_f4 + 32 * CH - 1) / (32 * CH);
     spmm_finish_kernel<CH><<<dim3((p.n_split + 7) / 8, fw), 256, 0, st>>>(p);
     LLMREC_CHECK_LAUNCH("spmm_finish");
@@ -519,7 +549,10 @@ extern "C" int llmrec_spmm_plan_tiles(const int32_t* rowptr_host, int32_t n_rows
         for (int32_t b = rowptr_host[r]; b < rowptr_host[r + 1]; b += tile_nnz) {
           int32_t* t = tiles_out + 8 * n_pieces++;
           t[0] = r; t[1] = 0; t[2] = b; t[3] = b + tile_nnz < rowptr_host[r + 1] ? b + tile_nnz : rowptr_host[r + 1];
-          t[4] = t[5] = t[6] = t[7] = 0;
+          t[4] = (int32_t)n_split;                                            // split index (ticket slot)
+          t[5] = split_first_out[n_split];                                    // first piece (tile id) of this row
+          t[6] = (rowptr_host[r + 1] - rowptr_host[r] + tile_nnz - 1) / tile_nnz;   // pieces of this row
+          t[7] = 0;
         }
       } else {
         n_pieces += (deg + tile_nnz - 1) / tile_nnz;
@@ -600,11 +633,13 @@ extern "C" int llmrec_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, co
     p.n_split_tiles = tiling->n_split_tiles; p.scratch = tiling->scratch;
     p.split_row = tiling->split_row; p.split_first = tiling->split_first; p.n_split = tiling->n_split;
     p.src_mask = tiling->src_mask;
+    p.split_tickets = ((p.total_f4 + 7) / 8 <= kTicketWindows) ? tiling->split_tickets : nullptr;
     LLMREC_CHECK_ARG(p.n_split == 0 || p.scratch != nullptr, "spmm: long-row pieces need the scratch buffer");
     int rc = 0;
     static const int bulk_mode = getenv("LLMREC_SPMM_BULK") ? atoi(getenv("LLMREC_SPMM_BULK")) : -1;   // -1 auto, 0 off, 1 on
     const bool bulk_ok = p.nseg == 1 && d == 128 && !p.src_mask && segs[s0].ldx == 128;
     if (bulk_ok && (bulk_mode == 1 || (bulk_mode == -1 && kSpmmBulkAuto && (int64_t)n_cols * 512 >= ((int64_t)576 << 20)))) {
+      p.split_tickets = nullptr;                                     // the staged kernel keeps the second-pass reduction of long rows
       const size_t smem = (size_t)kBulkWarps * kBulkStages * kBulkRows * 512 + kBulkWarps * kBulkStages * sizeof(uint64_t);
       static bool attr = false;
       if (!attr) { cudaFuncSetAttribute(spmm_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }

@@ -76,6 +76,8 @@ class TilePlan:
         self.tiles, self.split_row, self.split_first = (torch.from_numpy(a).to(dev) for a in (tiles, srow, sfirst))
         self.n_tiles, self.n_split, self.n_split_tiles = (int(c) for c in counts)
         self.tile_nnz, self.scratch = tile_nnz, None
+        # per (long row, column window) tickets: the last piece to finish reduces the row inside the same launch (self-resetting)
+        self.tickets = torch.zeros(max(self.n_split, 1) * 64, dtype=torch.int32, device=dev) if self.n_split else None
 
 
 class CsrOperator:
@@ -95,7 +97,7 @@ class CsrOperator:
             if k.scratch is not None:
                 _retired.append(k.scratch)
             k.scratch = torch.empty(need, dtype=torch.float32, device=self.rowptr.device)
-        return N.SpmmTiling(_p(k.tiles), _p(k.split_row), _p(k.split_first), _p(k.scratch), k.n_tiles, k.n_split, k.n_split_tiles, 0, None)
+        return N.SpmmTiling(_p(k.tiles), _p(k.split_row), _p(k.split_first), _p(k.scratch), k.n_tiles, k.n_split, k.n_split_tiles, 0, _p(k.tickets), None)
 
     def apply_rows(self, seg, rows, count, max_rows=None, src_mask=None, cta_per_row=False):
         """Row-list form (llmrec_spmm_rows_f32): only rows[0 .. count[0]) are computed and written.  seg = (X, Y, Z|None, softmax);
@@ -128,7 +130,7 @@ class CsrOperator:
         til.src_mask = src_mask.data_ptr() if src_mask is not None else None
         N.check(N.lib().llmrec_spmm_csr_f32(_p(self.rowptr), _p(self.col), _p(self.vals), _p(self.rs), _p(self.cs),
                                              self.n_rows, self.n_cols, d, arr, len(segs), C.byref(til), _stream()), "spmm")
-        _count(-(-len(segs) // N.MAX_SEG) * (2 if til.n_split > 0 else 1))
+        _count(-(-len(segs) // N.MAX_SEG))
 
 
 def row_softmax(X, out=None):
@@ -201,12 +203,12 @@ _scratch = {}
 _retired = []     # outgrown scratch buffers stay allocated: a captured CUDA graph may still hold their addresses
 
 
-def _get_scratch(key, n, device):
+def _get_scratch(key, n, device, zero=False):
     t = _scratch.get(key)
     if t is None or t.numel() < n:
         if t is not None:
             _retired.append(t)
-        t = _scratch[key] = torch.empty(max(int(n), 1), dtype=torch.float32, device=device)
+        t = _scratch[key] = (torch.zeros if zero else torch.empty)(max(int(n), 1), dtype=torch.float32, device=device)
     return t
 
 
@@ -222,7 +224,7 @@ def proj_fwd_group(problems, d, mode=0):
         ws = _get_scratch(("wsplit", W.data_ptr()), 2 * d * k, X.device) if mode == 0 else None
         arr[i] = N.ProjFwdProblem(_p(X), _p(W), _p(b), _p(out), _p(ws), _ld(X), _ld(out), n, k, 0)
     N.check(N.lib().llmrec_proj_fwd_group_f32(arr, len(problems), d, mode, _stream()), "proj_fwd_group")
-    _count(1 + len({int(p.W) for p in arr}) if mode == 0 else 1)
+    _count((2 if mode == 0 else 1) * -(-len(problems) // 8))
 
 
 def proj_fwd(X, W, b, out, mode=0):
@@ -241,9 +243,9 @@ def proj_wgrad_group(problems, d, mode=0):
             raise ValueError("proj_wgrad: bad shapes")
         arr[i] = N.ProjWgradProblem(_p(X), _p(dY), _p(dW), _p(db), _ld(X), _ld(dY), n, k, 1 if acc else 0)
     need = int(N.lib().llmrec_proj_wgrad_group_scratch(arr, len(problems), d, mode))
-    scratch = _get_scratch(("wgrad", problems[0][0].device.index), need, problems[0][0].device) if need else None
+    scratch = _get_scratch(("wgrad", problems[0][0].device.index), need, problems[0][0].device, zero=True) if need else None     # holds a ticket word
     N.check(N.lib().llmrec_proj_wgrad_group_f32(arr, len(problems), d, mode, _p(scratch), need, _stream()), "proj_wgrad_group")
-    _count(4 if need else len(problems))
+    _count(3 if need else len(problems))
 
 
 def proj_wgrad(X, dY, dW, db, accumulate=False, mode=0):
