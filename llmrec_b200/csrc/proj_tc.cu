@@ -601,9 +601,9 @@ int proj_wgrad_tc_group(const llmrec_proj_wgrad_problem* pr, int n_prob, int d, 
   P.total_items = items;
   const int64_t need = (int64_t)items * BM * d + (int64_t)n_prob * kColsumSlices * d + 4;
   LLMREC_CHECK_ARG(scratch && scratch_elems >= need, "proj_wgrad: scratch too small (%lld < %lld)", (long long)scratch_elems, (long long)need);
-  P.partial = scratch;
-  C.n_prob = n_prob; C.partial = scratch + (int64_t)items * BM * d;
-  C.ticket = reinterpret_cast<unsigned*>(scratch + need - 4);
+  P.partial = scratch + 4;                                   // word 0 of the scratch is the colsum ticket (fixed position for every problem set)
+  C.n_prob = n_prob; C.partial = scratch + 4 + (int64_t)items * BM * d;
+  C.ticket = reinterpret_cast<unsigned*>(scratch);
   uint32_t smem;
   P.stages = stages_for(d, split, &smem);
   P.tmem_cols = (int)pow2_cols(2 * d);
@@ -623,7 +623,7 @@ int proj_wgrad_tc_group(const llmrec_proj_wgrad_problem* pr, int n_prob, int d, 
   LLMREC_CHECK_LAUNCH("proj_wgrad_tc");
   ReduceParams R;
   memset(&R, 0, sizeof(R));
-  R.d = d; R.partial = scratch;
+  R.d = d; R.partial = scratch + 4;
   int blocks = 0;
   for (int p = 0; p < n_prob; ++p) {
     R.prob[p] = P.prob[p];
