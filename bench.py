@@ -411,6 +411,9 @@ def run_ours(a):
             torch.cuda.empty_cache()
         except Exception as e:                                        # an extra leg must never take the headline down
             cfgs[a.workload + "_hoisted"] = {"error": repr(e)[:300]}
+        if a.extra == 2:                                              # quick A/B runs: the hoisted line only
+            out["configs"] = cfgs
+            return out
         try:
             dsm, _, _ = run_workload(a.workload, a, K, W, min(a.min_seconds, 1.0), with_families=False, hoist=True, extra=["--device_sampler", "1"])
             cfgs[a.workload + "_hoisted_device_sampler"] = dict(dsm, note="--hoist_side 1 --device_sampler 1: batches drawn on the GPU inside the replayed graph "
@@ -480,7 +483,7 @@ def main():
     ap.add_argument("--host_sampler", default="native")
     ap.add_argument("--no-cpu", dest="no_cpu", action="store_true")
     ap.add_argument("--gpu-baseline", dest="gpu_baseline", type=int, default=1)
-    ap.add_argument("--extra", type=int, default=1, help="N=1: also measure the hoisted mode, the other small configuration and the synthetic 1-GPU scaling base")
+    ap.add_argument("--extra", type=int, default=1, help="N=1: also measure the hoisted mode, the other small configuration and the synthetic 1-GPU scaling base (2: the hoisted mode only)")
     ap.add_argument("--graph", type=int, default=1)
     ap.add_argument("--cpu-steps", dest="cpu_steps", type=int, default=24)
     ap.add_argument("--cpu-eval-users", dest="cpu_eval_users", type=int, default=1500)

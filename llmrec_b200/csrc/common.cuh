@@ -27,6 +27,15 @@ bool device_ok();
     }                                                                          \
   } while (0)
 
+#define LLMREC_CHECK_CUDA(expr)                                                \
+  do {                                                                         \
+    cudaError_t e__ = (expr);                                                  \
+    if (e__ != cudaSuccess) {                                                  \
+      llmrec::set_error("%s: %s", #expr, cudaGetErrorString(e__));             \
+      return 2;                                                                \
+    }                                                                          \
+  } while (0)
+
 #define LLMREC_REQUIRE_DEVICE()                                                       \
   do {                                                                                \
     if (!llmrec::device_ok()) {                                                       \

@@ -609,6 +609,32 @@ int proj_wgrad_tc_group(const llmrec_proj_wgrad_problem* pr, int n_prob, int d, 
   P.tmem_cols = (int)pow2_cols(2 * d);
   int grid = items < 148 ? items : 148;
   if (grid <= 0) return 0;
+  // The bias gradients depend on dY only: colsum runs as a BRANCH beside the persistent weight-gradient kernel (1 CTA of 512 threads per SM
+  // leaves room for its 256-thread blocks) -- fork/join through events, so inside a stream capture it becomes a parallel graph branch.
+  // The side stream and the two events are process-wide, created on first use (never during the call that is being captured in practice:
+  // callers run one eager step first); LLMREC_BRANCHES=0 keeps everything on `st`.
+  bool any_db = false;
+  for (int p = 0; p < n_prob; ++p) any_db = any_db || pr[p].db != nullptr;
+  static const bool branches = !(getenv("LLMREC_BRANCHES") && atoi(getenv("LLMREC_BRANCHES")) == 0);
+  static cudaStream_t side = nullptr;
+  static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool forked = false;
+  if (any_db) {
+    cudaStream_t cs = st;
+    if (branches) {
+      if (!side) {
+        LLMREC_CHECK_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+        LLMREC_CHECK_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        LLMREC_CHECK_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+      }
+      LLMREC_CHECK_CUDA(cudaEventRecord(ev_fork, st));
+      LLMREC_CHECK_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+      cs = side; forked = true;
+    }
+    colsum_kernel<<<dim3(kColsumSlices, n_prob), 256, 0, cs>>>(C);
+    LLMREC_CHECK_LAUNCH("colsum");
+    if (forked) LLMREC_CHECK_CUDA(cudaEventRecord(ev_join, side));
+  }
   static const bool force_v1 = getenv("LLMREC_PROJ_V1") != nullptr;
   if (split && d <= 128 && !force_v1) {
     int rc = proj_wgrad_ts_launch(P, grid, st);
@@ -640,12 +666,7 @@ int proj_wgrad_tc_group(const llmrec_proj_wgrad_problem* pr, int n_prob, int d, 
   for (int o = 0; o < R.n_out; ++o) { R.out[o].blk_start = blocks; blocks += ((R.out[o].k + BM - 1) / BM) * (BM / feats_per_blk); }
   wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(R);
   LLMREC_CHECK_LAUNCH("wgrad_reduce");
-  bool any_db = false;
-  for (int p = 0; p < n_prob; ++p) any_db = any_db || pr[p].db != nullptr;
-  if (any_db) {
-    colsum_kernel<<<dim3(kColsumSlices, n_prob), 256, 0, st>>>(C);
-    LLMREC_CHECK_LAUNCH("colsum");
-  }
+  if (forked) LLMREC_CHECK_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
   return 0;
 }
 

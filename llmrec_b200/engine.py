@@ -17,6 +17,7 @@ Every operand that shares a sparsity pattern rides in ONE SpMM launch (segments)
 from __future__ import annotations
 
 import contextlib
+import os
 from dataclasses import dataclass
 
 import torch
@@ -111,9 +112,32 @@ class HotPath:
         self.pre_step_undo = None         # undoes the side effect of ONE pre_step (the warm-up step before a capture must not consume a batch)
         self.opt = None
         self.timer = None
+        # independent launches of a step run as BRANCHES: a side stream forked from / joined into the current one with events, so the
+        # captured step is a graph with parallel nodes (LLMREC_BRANCHES=0: one chain; off on CPU stand-ins and under the span timer)
+        self.branches = dev.type == "cuda" and os.environ.get("LLMREC_BRANCHES", "1") != "0"
+        self._side, self._forked = None, False
 
     def _t(self, name):
         return self.timer.span(name) if self.timer is not None else contextlib.nullcontext()
+
+    # ---- branches -------------------------------------------------------------------------------
+    def _fork(self, thunk):
+        """Run `thunk` on the side stream, ordered after everything enqueued on the current stream so far; `_join` orders the current
+        stream behind it.  Every buffer a branch touches is a persistent engine buffer, so no allocator bookkeeping is needed."""
+        if not self.branches or self.timer is not None:
+            thunk()
+            return
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.E_u.device)
+        self._side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._side):
+            thunk()
+        self._forked = True
+
+    def _join(self):
+        if self._forked:
+            torch.cuda.current_stream().wait_stream(self._side)
+            self._forked = False
 
     # ---- column-block views ------------------------------------------------------------------
     def blk(self, buf, s):
@@ -149,10 +173,14 @@ class HotPath:
                 probs.sort(key=lambda t: -t[0].shape[1])                       # long-K tiles first
                 ops.proj_fwd_group(probs, d, m)
 
-    def _prop_fwd(self, with_feats=None):
-        """with_feats=False: the ID layers only (the hoisted mode propagates no side-feature operand)."""
+    def _prop_fwd(self, with_feats=None, after_sides=None):
+        """with_feats=False: the ID layers only (the hoisted mode propagates no side-feature operand).
+        after_sides: called once Fu and Fi exist (after the second product; at once without side features) -- train_step forks the
+        first touch of the gradient buffers there."""
         L, S = self.L, self.S
         wf = self.has_feats if with_feats is None else with_feats
+        if after_sides is not None and not wf:
+            after_sides()
         # step t even: ui (I_{t/2} -> U_{t/2+1});  t odd: iu (U_{(t+1)/2} -> I_{(t+1)/2}); softmax on the last layer
         n_steps = max(2 * L, 3 if wf else 0)
         for t in range(n_steps):
@@ -176,6 +204,8 @@ class HotPath:
                     segs.append((self.Ul[l], self.Il[l], None, l == L))                                                # :175,180
                 with self._t("spmm_fwd"):
                     self.iu.apply(segs)
+                if after_sides is not None and wf and t == 1:
+                    after_sides()
 
     def _fuse_fwd(self):
         c = self.cfg
@@ -186,8 +216,9 @@ class HotPath:
         else:
             coefs, su, si = [], [], []
         with self._t("fuse_fwd"):
-            ops.fuse_fwd(self.Ul, su, coefs, self.U)                                                                   # :185-197
+            self._fork(lambda: ops.fuse_fwd(self.Ul, su, coefs, self.U))                                               # :185-197
             ops.fuse_fwd(self.Il, si, coefs, self.I)
+            self._join()
         self._fuse_args = (coefs, su, si)
 
     # ---- backward: expects gU, gI and (GFu, GFi, Gprof_u, Gprof_i, GP_usr_direct) filled ---------------
@@ -206,8 +237,9 @@ class HotPath:
         else:
             dsu, dsi = [], []
         with self._t("fuse_bwd"):
-            ops.fuse_bwd(self.gU, L + 1, self.dUl, su, coefs, dsu, True)
+            self._fork(lambda: ops.fuse_bwd(self.gU, L + 1, self.dUl, su, coefs, dsu, True))
             ops.fuse_bwd(self.gI, L + 1, self.dIl, si, coefs, dsi, True)
+            self._join()
 
     def _chain_bwd(self, gp_usr_direct=None, gpi_direct=None, with_feats=None):
         L, S = self.L, self.S
@@ -278,39 +310,50 @@ class HotPath:
         self._meta_table = torch.tensor([[b, k] for b, k in enumerate(keep)], dtype=torch.int32).to(dev)
         self._bpr_work = ops.bpr_work(self.n_heads, self._cap, dev)
 
-    def loss_and_output_grads(self, users, pos, neg, meta=None):
+    def loss_and_output_grads(self, users, pos, neg, meta=None, init_done=False):
         """users/pos/neg: int32 CUDA tensors of equal length B' (sampled + augmented triplets) -- or, with `meta` (int32 CUDA
-        {B', n_keep}), capacity-sized buffers whose first B' entries are live (the CUDA-graph path)."""
+        {B', n_keep}), capacity-sized buffers whose first B' entries are live (the CUDA-graph path).
+        init_done: `_grad_init` already ran for this step (train_step forks it beside the tail of the forward pass)."""
         c = self.cfg
         B = int(users.numel())
         self.ensure_capacity(max(B, self.batch_capacity()))
         n_keep = int((1 - c.prune_loss_drop_rate) * B)                     # main.py:161-162 (double arithmetic)
         heads = [(self.U, self.I, self.gU, self.gI, 1.0, 1.0)]                                                        # main.py:232-235
-        regions = [(self.gU, None, 0.0), (self.gI, None, 0.0)]
         if self.has_feats:
-            creg = c.feat_reg_decay / self.ni                                                                          # main.py:151-156
-            d2 = 2 * self.d
-            # first touch of the gradient buffers: feat_reg gradient c*X on the image/text blocks (its value starts the loss), zeros elsewhere
-            regions += [(self.GFu[:, :d2], self.Fu[:, :d2], creg), (self.GFi[:, :d2], self.Fi[:, :d2], creg),
-                        (self.Gprof_u, None, 0.0), (self.Gprof_i, None, 0.0)]
-            if self.S > 2:
-                regions += [(self.GFu[:, d2:], None, 0.0), (self.GFi[:, d2:], None, 0.0)]
             heads.append((self.blk(self.Fu, 0), self.blk(self.Fi, 0), self.blk(self.GFu, 0), self.blk(self.GFi, 0), c.mm_mf_rate, 0.0))  # :238-241
             heads.append((self.blk(self.Fu, 1), self.blk(self.Fi, 1), self.blk(self.GFu, 1), self.blk(self.GFi, 1), c.mm_mf_rate, 0.0))  # :242-246
             for j in range(len(self.keys)):                                                                            # :248-254
                 heads.append((self.prof_u, self.blk(self.Fi, 2 + j), self.Gprof_u, self.blk(self.GFi, 2 + j), c.aug_mf_rate, 0.0))
-        with self._t("grad_init"):
-            ops.grad_init(regions, self.loss)
+        if not init_done:
+            self._grad_init()
         with self._t("bpr"):
             ops.bpr_heads(heads, users, pos, neg, n_keep, c.regs0 / c.batch_size, self.head_out, self.loss, self._bpr_work, meta=meta)
         return self.loss
+
+    def _grad_init(self):
+        """First touch of every gradient buffer the loss heads accumulate into: the feat_reg gradient c*X on the image/text blocks (its
+        value starts the loss, main.py:151-156), zeros elsewhere.  Needs Fu / Fi only, not the fused outputs."""
+        c = self.cfg
+        regions = [(self.gU, None, 0.0), (self.gI, None, 0.0)]
+        if self.has_feats:
+            creg = c.feat_reg_decay / self.ni
+            d2 = 2 * self.d
+            regions += [(self.GFu[:, :d2], self.Fu[:, :d2], creg), (self.GFi[:, :d2], self.Fi[:, :d2], creg),
+                        (self.Gprof_u, None, 0.0), (self.Gprof_i, None, 0.0)]
+            if self.S > 2:
+                regions += [(self.GFu[:, d2:], None, 0.0), (self.GFi[:, d2:], None, 0.0)]
+        with self._t("grad_init"):
+            ops.grad_init(regions, self.loss)
 
     def train_step(self, users, pos, neg, meta=None):
         """forward + losses + backward + AdamW; everything stays on the current stream."""
         if self.opt is None:
             raise RuntimeError("attach an optimizer with set_optimizer() first")
-        self.forward()
-        self.loss_and_output_grads(users, pos, neg, meta)
+        self._proj_fwd()
+        self._prop_fwd(after_sides=lambda: self._fork(self._grad_init))      # branch: runs beside the remaining products and the fusion
+        self._fuse_fwd()                                                     # joins
+        self._join()
+        self.loss_and_output_grads(users, pos, neg, meta, init_done=True)
         self.backward()
         with self._t("adamw"):
             self.opt.step([self.grads[k] for k in self._opt_names])

@@ -131,8 +131,27 @@ class HoistedHotPath(HotPath):
             pn[:cap].copy_(pos); pn[cap:].copy_(neg)
         blk = lambda buf, s: buf[:, s * d:(s + 1) * d]
         tab = lambda X, j: X[:, self.col0[j]:self.col0[j] + self.widths[j]]
-        # ---- forward ----
-        self._prop_fwd(with_feats=False)                                                      # ID layers (Models.py:169-183)
+        g = self.grads
+        creg = cfg.feat_reg_decay / self.ni
+        reg_names = ("image_trans", "text_trans")
+
+        # ---- branch: first touch of the gradient buffers, feat_reg, ID layers  ||  main: the batch's side-feature rows ----
+        def id_branch():
+            # feat_reg (main.py:151-156) and its gradient depend on the parameters only (Gram form): they are written FIRST into zeroed
+            # weight / bias gradients; the batch terms below accumulate on top
+            zero = [(c["gU"], None, 0.0), (c["gI"], None, 0.0), (c["GFu"], None, 0.0), (c["GFi"], None, 0.0), (c["Gpu"], None, 0.0),
+                    (c["Gpi"], None, 0.0), (self.dUl, None, 0.0), (self.dIl, None, 0.0)]
+            for name in reg_names:
+                zero += [(g[name + ".weight"], None, 0.0), (g[name + ".bias"].view(1, -1), None, 0.0)]
+            with self._t("grad_init"):
+                ops.grad_init(zero, self.loss)
+            with self._t("feat_reg"):
+                for j, name in enumerate(reg_names):
+                    G, h, n2 = self.gram[j]
+                    ops.feat_reg_gram(p[name + ".weight"], p[name + ".bias"], G, h, n2, creg, g[name + ".weight"], g[name + ".bias"], self.loss)
+            self._prop_fwd(with_feats=False)                                                  # ID layers (Models.py:169-183)
+
+        self._fork(id_branch)
         with self._t("gather"):
             ops.gather_rows(self.TU, users, c["Xu"])
             ops.gather_rows(self.TI, pn, c["Xi"])
@@ -148,16 +167,15 @@ class HoistedHotPath(HotPath):
         with self._t("proj_fwd"):
             ops.proj_fwd_group(probs, d, m)                                                   # Models.py:145-167 on the batch's rows
             ops.rank1_add(r1)
+        self._join()
         coefs = [cfg.model_cat_rate, cfg.model_cat_rate, cfg.user_cat_rate] + [cfg.item_cat_rate] * len(self.keys)
         su = [blk(c["Fu"], 0), blk(c["Fu"], 1), c["pu"]] + [blk(c["Fu"], 2 + j) for j in range(len(self.keys))]
         si = [blk(c["Fi"], 0), blk(c["Fi"], 1), c["pi"]] + [blk(c["Fi"], 2 + j) for j in range(len(self.keys))]
         with self._t("fuse_fwd"):
-            ops.fuse_fwd(self.Ul, su, coefs, c["U"], rows=users, compact=True)                # :185-197 on the batch's rows
+            self._fork(lambda: ops.fuse_fwd(self.Ul, su, coefs, c["U"], rows=users, compact=True))   # :185-197 on the batch's rows
             ops.fuse_fwd(self.Il, si, coefs, c["I"], rows=pn, compact=True)
+            self._join()
         # ---- losses + output gradients ----
-        with self._t("grad_init"):
-            ops.grad_init([(c["gU"], None, 0.0), (c["gI"], None, 0.0), (c["GFu"], None, 0.0), (c["GFi"], None, 0.0), (c["Gpu"], None, 0.0),
-                           (c["Gpi"], None, 0.0), (self.dUl, None, 0.0), (self.dIl, None, 0.0)], self.loss)
         heads = [(c["U"], c["I"], c["gU"], c["gI"], 1.0, 1.0),                                                         # main.py:232-235
                  (blk(c["Fu"], 0), blk(c["Fi"], 0), blk(c["GFu"], 0), blk(c["GFi"], 0), cfg.mm_mf_rate, 0.0),        # :238-241
                  (blk(c["Fu"], 1), blk(c["Fi"], 1), blk(c["GFu"], 1), blk(c["GFi"], 1), cfg.mm_mf_rate, 0.0)]        # :242-246
@@ -169,15 +187,19 @@ class HoistedHotPath(HotPath):
         # ---- backward: fusion on the compact rows, ID gradients scattered into the dense chain ----
         dsu = [blk(c["GFu"], 0), blk(c["GFu"], 1), c["Gpu"]] + [blk(c["GFu"], 2 + j) for j in range(len(self.keys))]
         dsi = [blk(c["GFi"], 0), blk(c["GFi"], 1), c["Gpi"]] + [blk(c["GFi"], 2 + j) for j in range(len(self.keys))]
-        with self._t("fuse_bwd"):
+
+        def user_side_bwd():
             ops.fuse_bwd(c["gU"], L + 1, c["dU"], su, coefs, dsu, True)
-            ops.fuse_bwd(c["gI"], L + 1, c["dI"], si, coefs, dsi, True)
             ops.scatter_add_rows(c["dU"], users, self.dUl)                                    # rows past B' carry zero gradients
+
+        with self._t("fuse_bwd"):
+            self._fork(user_side_bwd)
+            ops.fuse_bwd(c["gI"], L + 1, c["dI"], si, coefs, dsi, True)
             ops.scatter_add_rows(c["dI"], pn, self.dIl)
-        self._chain_bwd(with_feats=False)
-        # ---- weight gradients from the compact rows (+ feat_reg through the Gram matrices) ----
-        g = self.grads
-        wg, seen = [], set()
+            self._join()
+        # ---- branch: the dense ID chain  ||  main: weight / bias gradients from the compact rows ----
+        self._fork(lambda: self._chain_bwd(with_feats=False))
+        wg, seen = [], set(reg_names)                             # image / text gradients already hold the feat_reg term
         bias_terms = {}
         for j in list(range(S)) + [S]:
             name = self.w_names[j] if j < S else "user_trans"
@@ -187,14 +209,10 @@ class HoistedHotPath(HotPath):
             wg.append((tab(c["Xi"], j), dYi, g[name + ".weight"], None, True))
             bias_terms.setdefault(name, []).extend([(dYu, c["Xu"][:, scol]), (dYi, c["Xi"][:, scol])])
         with self._t("proj_wgrad"):
-            ops.proj_wgrad_group(wg, d, m)
             for name, terms in bias_terms.items():
-                ops.scaled_colsum(terms, g[name + ".bias"], accumulate=False)
-        creg = cfg.feat_reg_decay / self.ni
-        with self._t("feat_reg"):
-            for j, name in enumerate(("image_trans", "text_trans")):
-                G, h, n2 = self.gram[j]
-                ops.feat_reg_gram(p[name + ".weight"], p[name + ".bias"], G, h, n2, creg, g[name + ".weight"], g[name + ".bias"], self.loss)
+                ops.scaled_colsum(terms, g[name + ".bias"], accumulate=name in reg_names)
+            ops.proj_wgrad_group(wg, d, m)
+        self._join()
         with self._t("adamw"):
             self.opt.step([self.grads[k] for k in self._opt_names])
         return self.loss
