@@ -115,29 +115,37 @@ class HotPath:
         # independent launches of a step run as BRANCHES: a side stream forked from / joined into the current one with events, so the
         # captured step is a graph with parallel nodes (LLMREC_BRANCHES=0: one chain; off on CPU stand-ins and under the span timer)
         self.branches = dev.type == "cuda" and os.environ.get("LLMREC_BRANCHES", "1") != "0"
-        self._side, self._forked = None, False
+        self._side, self._forked = {}, set()
 
     def _t(self, name):
         return self.timer.span(name) if self.timer is not None else contextlib.nullcontext()
 
     # ---- branches -------------------------------------------------------------------------------
-    def _fork(self, thunk):
-        """Run `thunk` on the side stream, ordered after everything enqueued on the current stream so far; `_join` orders the current
-        stream behind it.  Every buffer a branch touches is a persistent engine buffer, so no allocator bookkeeping is needed."""
+    def _fork(self, thunk, lane=0):
+        """Run `thunk` on side stream `lane`, ordered after everything enqueued on the current stream so far; `_join` orders the current
+        stream behind every lane used since the last join.  Every buffer a branch touches is a persistent engine buffer, so no allocator
+        bookkeeping is needed."""
         if not self.branches or self.timer is not None:
             thunk()
             return
-        if self._side is None:
-            self._side = torch.cuda.Stream(device=self.E_u.device)
-        self._side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(self._side):
+        st = self._side.get(lane)
+        if st is None:
+            st = self._side[lane] = torch.cuda.Stream(device=self.E_u.device)
+        st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st):
             thunk()
-        self._forked = True
+        self._forked.add(lane)
+
+    def _id_opset(self):
+        """(ui, iu, uiT, iuT) with their own long-row scratch / tickets: launches through them may overlap launches of the primary set."""
+        if getattr(self, "_ids", None) is None:
+            self._ids = tuple(o.branch() for o in (self.ui, self.iu, self.uiT, self.iuT))
+        return self._ids
 
     def _join(self):
-        if self._forked:
-            torch.cuda.current_stream().wait_stream(self._side)
-            self._forked = False
+        for lane in sorted(self._forked):
+            torch.cuda.current_stream().wait_stream(self._side[lane])
+        self._forked.clear()
 
     # ---- column-block views ------------------------------------------------------------------
     def blk(self, buf, s):
@@ -173,16 +181,18 @@ class HotPath:
                 probs.sort(key=lambda t: -t[0].shape[1])                       # long-K tiles first
                 ops.proj_fwd_group(probs, d, m)
 
-    def _prop_fwd(self, with_feats=None, after_sides=None):
-        """with_feats=False: the ID layers only (the hoisted mode propagates no side-feature operand).
+    def _prop_fwd(self, with_feats=None, after_sides=None, with_ids=True, opset=None):
+        """with_feats=False: the ID layers only (the hoisted mode propagates no side-feature operand); with_ids=False: the side-feature
+        operands only (train_step runs the ID layers as a branch beside the projections).  opset: (ui, iu) to launch through.
         after_sides: called once Fu and Fi exist (after the second product; at once without side features) -- train_step forks the
         first touch of the gradient buffers there."""
         L, S = self.L, self.S
         wf = self.has_feats if with_feats is None else with_feats
+        ui, iu = (self.ui, self.iu) if opset is None else opset
         if after_sides is not None and not wf:
             after_sides()
         # step t even: ui (I_{t/2} -> U_{t/2+1});  t odd: iu (U_{(t+1)/2} -> I_{(t+1)/2}); softmax on the last layer
-        n_steps = max(2 * L, 3 if wf else 0)
+        n_steps = max(2 * L if with_ids else 0, 3 if wf else 0)
         for t in range(n_steps):
             segs = []
             if t % 2 == 0:
@@ -191,19 +201,19 @@ class HotPath:
                     segs += [(self.blk(self.Pi, s), self.blk(self.Fu, s), None, False) for s in range(S)]                # :153,156,162
                 if wf and t == 2:
                     segs.append((self.prof_i, self.prof_u, None, False))                                               # :167
-                if l <= L:
+                if with_ids and l <= L:
                     segs.append((self.Il[l - 1], self.Ul[l], None, l == L))                                            # :174,178
                 with self._t("spmm_fwd"):
-                    self.ui.apply(segs)
+                    ui.apply(segs)
             else:
                 l = (t + 1) // 2
                 if wf and t == 1:
                     segs += [(self.blk(self.Fu, s), self.blk(self.Fi, s), None, False) for s in range(S)]                # :154,157,163
                     segs.append((self.P_usr, self.prof_i, None, False))                                                # :166
-                if l <= L:
+                if with_ids and l <= L:
                     segs.append((self.Ul[l], self.Il[l], None, l == L))                                                # :175,180
                 with self._t("spmm_fwd"):
-                    self.iu.apply(segs)
+                    iu.apply(segs)
                 if after_sides is not None and wf and t == 1:
                     after_sides()
 
@@ -241,39 +251,47 @@ class HotPath:
             ops.fuse_bwd(self.gI, L + 1, self.dIl, si, coefs, dsi, True)
             self._join()
 
-    def _chain_bwd(self, gp_usr_direct=None, gpi_direct=None, with_feats=None):
+    def _chain_bwd(self, gp_usr_direct=None, gpi_direct=None, with_feats=None, with_ids=True, opset=None):
+        """with_feats=False: the ID chain only; with_ids=False: the side-feature operands only; opset: (uiT, iuT) to launch through."""
         L, S = self.L, self.S
         wf = self.has_feats if with_feats is None else with_feats
+        uiT, iuT = (self.uiT, self.iuT) if opset is None else opset
         if wf:
             # prof_u = ui . prof_i  ->  Gprof_i += ui^T Gprof_u
             with self._t("spmm_bwd"):
-                self.uiT.apply([(self.Gprof_u, self.Gprof_i, self.Gprof_i, False)])
+                uiT.apply([(self.Gprof_u, self.Gprof_i, self.Gprof_i, False)])
         gE_i = self.grads["item_id_embedding.weight"]
         g_cur_I = self.dIl
         for l in range(L, 0, -1):
+            if not with_ids and l < L:
+                break
             # I_l = [softmax] iu . U_l
-            if l == L:
-                with self._t("softmax_bwd"):
-                    src = ops.row_softmax_bwd(self.Il[l], g_cur_I, out=self.tmpI)
-            else:
-                src = g_cur_I
-            segs = [(src, self.bufU, self.dUl, False)]
+            segs = []
+            if with_ids:
+                if l == L:
+                    with self._t("softmax_bwd"):
+                        src = ops.row_softmax_bwd(self.Il[l], g_cur_I, out=self.tmpI)
+                else:
+                    src = g_cur_I
+                segs.append((src, self.bufU, self.dUl, False))
             if wf and l == L:
                 segs += [(self.blk(self.GFi, s), self.blk(self.GFu, s), self.blk(self.GFu, s), False) for s in range(S)]
                 segs.append((self.Gprof_i, self.GP_usr, gp_usr_direct, False))
             with self._t("spmm_bwd"):
-                self.iuT.apply(segs)
+                iuT.apply(segs)
             # U_l = [softmax] ui . I_{l-1}
-            if l == L:
-                with self._t("softmax_bwd"):
-                    ops.row_softmax_bwd(self.Ul[l], self.bufU, out=self.bufU)
+            segs = []
             dst = gE_i if l == 1 else self.bufI
-            segs = [(self.bufU, dst, self.dIl, False)]
+            if with_ids:
+                if l == L:
+                    with self._t("softmax_bwd"):
+                        ops.row_softmax_bwd(self.Ul[l], self.bufU, out=self.bufU)
+                segs.append((self.bufU, dst, self.dIl, False))
             if wf and l == L:
                 segs += [(self.blk(self.GFu, s), self.blk(self.GPi, s), self.blk(gpi_direct, s) if gpi_direct is not None else None, False)
                          for s in range(S)]
             with self._t("spmm_bwd"):
-                self.uiT.apply(segs)
+                uiT.apply(segs)
             g_cur_I = dst
 
     def _wgrad(self):
@@ -349,12 +367,36 @@ class HotPath:
         """forward + losses + backward + AdamW; everything stays on the current stream."""
         if self.opt is None:
             raise RuntimeError("attach an optimizer with set_optimizer() first")
-        self._proj_fwd()
-        self._prop_fwd(after_sides=lambda: self._fork(self._grad_init))      # branch: runs beside the remaining products and the fusion
+        split = self.has_feats and self.branches and self.timer is None
+        if split:
+            # the ID layers do not depend on the projections: they run as a branch (through operators with their own long-row scratch)
+            # beside the projection kernel and the side-feature products; the first touch of the gradient buffers follows on the branch
+            ids = self._id_opset()
+            if getattr(self, "_ev_ids", None) is None:
+                self._ev_ids = torch.cuda.Event()
+
+            def id_layers():
+                self._prop_fwd(with_feats=False, opset=ids[:2])
+                self._ev_ids.record()                                        # on the branch
+
+            self._fork(id_layers)
+            self._proj_fwd()
+            self._prop_fwd(with_ids=False, after_sides=lambda: self._fork(self._grad_init))
+            torch.cuda.current_stream().wait_event(self._ev_ids)             # the item-side fusion below reads Il; grad_init may still run
+        else:
+            self._proj_fwd()
+            self._prop_fwd(after_sides=lambda: self._fork(self._grad_init))  # branch: runs beside the remaining products and the fusion
         self._fuse_fwd()                                                     # joins
         self._join()
         self.loss_and_output_grads(users, pos, neg, meta, init_done=True)
-        self.backward()
+        if split:
+            self._fuse_bwd()
+            self._fork(lambda: self._chain_bwd(with_feats=False, opset=ids[2:]))    # ID chain || side-feature chain + weight gradients
+            self._chain_bwd(with_ids=False)
+            self._wgrad()
+            self._join()
+        else:
+            self.backward()
         with self._t("adamw"):
             self.opt.step([self.grads[k] for k in self._opt_names])
         return self.loss

@@ -135,8 +135,8 @@ class HoistedHotPath(HotPath):
         creg = cfg.feat_reg_decay / self.ni
         reg_names = ("image_trans", "text_trans")
 
-        # ---- branch: first touch of the gradient buffers, feat_reg, ID layers  ||  main: the batch's side-feature rows ----
-        def id_branch():
+        # ---- branches: ID layers | first touch of the gradient buffers + feat_reg  ||  main: the batch's side-feature rows ----
+        def init_branch():
             # feat_reg (main.py:151-156) and its gradient depend on the parameters only (Gram form): they are written FIRST into zeroed
             # weight / bias gradients; the batch terms below accumulate on top
             zero = [(c["gU"], None, 0.0), (c["gI"], None, 0.0), (c["GFu"], None, 0.0), (c["GFi"], None, 0.0), (c["Gpu"], None, 0.0),
@@ -149,9 +149,9 @@ class HoistedHotPath(HotPath):
                 for j, name in enumerate(reg_names):
                     G, h, n2 = self.gram[j]
                     ops.feat_reg_gram(p[name + ".weight"], p[name + ".bias"], G, h, n2, creg, g[name + ".weight"], g[name + ".bias"], self.loss)
-            self._prop_fwd(with_feats=False)                                                  # ID layers (Models.py:169-183)
 
-        self._fork(id_branch)
+        self._fork(lambda: self._prop_fwd(with_feats=False), lane=0)                          # ID layers (Models.py:169-183)
+        self._fork(init_branch, lane=1)
         with self._t("gather"):
             ops.gather_rows(self.TU, users, c["Xu"])
             ops.gather_rows(self.TI, pn, c["Xi"])
@@ -198,7 +198,7 @@ class HoistedHotPath(HotPath):
             ops.scatter_add_rows(c["dI"], pn, self.dIl)
             self._join()
         # ---- branch: the dense ID chain  ||  main: weight / bias gradients from the compact rows ----
-        self._fork(lambda: self._chain_bwd(with_feats=False))
+        self._fork(lambda: self._chain_bwd(with_feats=False), lane=0)
         wg, seen = [], set(reg_names)                             # image / text gradients already hold the feat_reg term
         bias_terms = {}
         for j in list(range(S)) + [S]:
@@ -208,9 +208,12 @@ class HoistedHotPath(HotPath):
             wg.append((tab(c["Xu"], j), dYu, g[name + ".weight"], None, name in seen)); seen.add(name)
             wg.append((tab(c["Xi"], j), dYi, g[name + ".weight"], None, True))
             bias_terms.setdefault(name, []).extend([(dYu, c["Xu"][:, scol]), (dYi, c["Xi"][:, scol])])
-        with self._t("proj_wgrad"):
+        def bias_grads():
             for name, terms in bias_terms.items():
                 ops.scaled_colsum(terms, g[name + ".bias"], accumulate=name in reg_names)
+
+        with self._t("proj_wgrad"):
+            self._fork(bias_grads, lane=1)
             ops.proj_wgrad_group(wg, d, m)
         self._join()
         with self._t("adamw"):

@@ -6,6 +6,7 @@ launches of the hand-written sm_100a kernels.  2-D operands must be row-major vi
 """
 from __future__ import annotations
 
+import copy
 import ctypes as C
 import os
 
@@ -89,6 +90,15 @@ class CsrOperator:
         self.n_rows, self.n_cols = int(n_rows), int(n_cols)
         self.nnz = int(col.numel())
         self.plan = plan if plan is not None else TilePlan(self.rowptr, self.n_rows, tile_nnz)
+
+    def branch(self):
+        """The same operator with its own long-row scratch and tickets, for launches that may overlap launches of `self` (or of an
+        operator sharing its plan) on another stream."""
+        o, k = copy.copy(self), copy.copy(self.plan)
+        k.scratch = None
+        k.tickets = torch.zeros_like(self.plan.tickets) if self.plan.tickets is not None else None
+        o.plan = k
+        return o
 
     def _tiling_struct(self, width):
         k = self.plan

@@ -7,7 +7,7 @@ O=gpurun_out/r2ab
 mkdir -p $O
 python -m llmrec_b200.build > $O/build.log 2>&1
 timeout 1200 python -m pytest tests -q -m gpu > $O/pytest_gpu.log 2>&1; tail -4 $O/pytest_gpu.log
-for v in $A $B $A $B; do
+for v in $A $B; do
   env $VAR=$v timeout 600 python bench.py --no-cpu --gpu-baseline 0 --extra 2 > $O/bench_$v.json 2> $O/bench_$v.err
   python - <<PY
 import json
