@@ -611,13 +611,19 @@ int proj_wgrad_tc_group(const llmrec_proj_wgrad_problem* pr, int n_prob, int d, 
   if (grid <= 0) return 0;
   // The bias gradients depend on dY only: colsum runs as a BRANCH beside the persistent weight-gradient kernel (1 CTA of 512 threads per SM
   // leaves room for its 256-thread blocks) -- fork/join through events, so inside a stream capture it becomes a parallel graph branch.
-  // The side stream and the two events are process-wide, created on first use (never during the call that is being captured in practice:
+  // The side stream and the two events are per device, created on first use (never during the call that is being captured in practice:
   // callers run one eager step first); LLMREC_BRANCHES=0 keeps everything on `st`.
   bool any_db = false;
   for (int p = 0; p < n_prob; ++p) any_db = any_db || pr[p].db != nullptr;
   static const bool branches = !(getenv("LLMREC_BRANCHES") && atoi(getenv("LLMREC_BRANCHES")) == 0);
-  static cudaStream_t side = nullptr;
-  static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  struct Branch { cudaStream_t side; cudaEvent_t fork, join; };
+  static Branch per_device[64] = {};                      // one side stream + event pair per device the process drives
+  int dev = 0;
+  LLMREC_CHECK_CUDA(cudaGetDevice(&dev));
+  LLMREC_CHECK_ARG(dev >= 0 && dev < 64, "proj_wgrad: device ordinal %d out of range", dev);
+  cudaStream_t& side = per_device[dev].side;
+  cudaEvent_t& ev_fork = per_device[dev].fork;
+  cudaEvent_t& ev_join = per_device[dev].join;
   bool forked = false;
   if (any_db) {
     cudaStream_t cs = st;

@@ -15,6 +15,9 @@ class CsrOperator:
         self.plan = plan if plan is not None else object()
         assert self.rowptr.numel() == self.n_rows + 1
 
+    def branch(self):                                    # own long-row scratch on the device; nothing to copy here
+        return self
+
     def apply_rows(self, seg, rows, count, max_rows=None, src_mask=None, cta_per_row=False):          # llmrec_spmm_rows_f32: listed rows only
         X, Y, Z, sm = seg
         full = torch.empty_like(Y)

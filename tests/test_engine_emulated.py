@@ -23,7 +23,7 @@ def _worker(rank, ddir, out):
     from oracle import llmrec_oracle as O
     data = O.load_dataset(ddir)
     ok = True
-    for weight_size, d in (("[64, 64]", 64), ("[32,32,32]", 32)):
+    for weight_size, d, split in (("[64, 64]", 64, False), ("[32,32,32]", 32, False), ("[64, 64]", 64, True), ("[32,32,32]", 32, True)):
         ocfg = O.OracleConfig(batch_size=128, embed_size=d, weight_size=eval(weight_size), lr=1e-3)
         O.set_seed(2022)
         otr = O.OracleTrainer(data, ocfg)
@@ -34,6 +34,7 @@ def _worker(rank, ddir, out):
         cfg = HotPathConfig(embed_size=d, n_layers=len(eval(weight_size)), batch_size=128)
         hp = HotPath((g.ui, g.iu, g.uiT, g.iuT), params, feats, cfg)
         hp.set_optimizer(lr=1e-3)
+        hp.force_split = split              # the branch schedule of train_step (ID layers | user-profile operand | side features), run in line
         O.set_seed(7)
         for step in range(3):
             users, pos, neg = O.sample_batch(data, ocfg)
