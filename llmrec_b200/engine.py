@@ -184,10 +184,9 @@ class HotPath:
                 probs.sort(key=lambda t: -t[0].shape[1])                       # long-K tiles first
                 ops.proj_fwd_group(probs, d, m)
 
-    def _prop_fwd(self, with_feats=None, after_sides=None, with_ids=True, opset=None, with_prof=True):
+    def _prop_fwd(self, with_feats=None, after_sides=None, with_ids=True, opset=None):
         """with_feats=False: the ID layers only (the hoisted mode propagates no side-feature operand); with_ids=False: the side-feature
-        operands only (train_step runs the ID layers as a branch beside the projections); with_prof=False: without the user-profile operand
-        (`_prof_fwd` runs it as its own branch).  opset: (ui, iu) to launch through.
+        operands only (train_step runs the ID layers as a branch beside the projections).  opset: (ui, iu) to launch through.
         after_sides: called once Fu and Fi exist (after the second product; at once without side features) -- train_step forks the
         first touch of the gradient buffers there."""
         L, S = self.L, self.S
@@ -196,14 +195,14 @@ class HotPath:
         if after_sides is not None and not wf:
             after_sides()
         # step t even: ui (I_{t/2} -> U_{t/2+1});  t odd: iu (U_{(t+1)/2} -> I_{(t+1)/2}); softmax on the last layer
-        n_steps = max(2 * L if with_ids else 0, (3 if with_prof else 2) if wf else 0)
+        n_steps = max(2 * L if with_ids else 0, 3 if wf else 0)
         for t in range(n_steps):
             segs = []
             if t % 2 == 0:
                 l = t // 2 + 1
                 if wf and t == 0:
                     segs += [(self.blk(self.Pi, s), self.blk(self.Fu, s), None, False) for s in range(S)]                # :153,156,162
-                if wf and with_prof and t == 2:
+                if wf and t == 2:
                     segs.append((self.prof_i, self.prof_u, None, False))                                               # :167
                 if with_ids and l <= L:
                     segs.append((self.Il[l - 1], self.Ul[l], None, l == L))                                            # :174,178
@@ -213,28 +212,13 @@ class HotPath:
                 l = (t + 1) // 2
                 if wf and t == 1:
                     segs += [(self.blk(self.Fu, s), self.blk(self.Fi, s), None, False) for s in range(S)]                # :154,157,163
-                    if with_prof:
-                        segs.append((self.P_usr, self.prof_i, None, False))                                            # :166
+                    segs.append((self.P_usr, self.prof_i, None, False))                                                # :166
                 if with_ids and l <= L:
                     segs.append((self.Ul[l], self.Il[l], None, l == L))                                                # :175,180
                 with self._t("spmm_fwd"):
                     iu.apply(segs)
                 if after_sides is not None and wf and t == 1:
                     after_sides()
-
-    def _prof_fwd(self, opset):
-        """prof_i = iu . P_usr, prof_u = ui . prof_i (Models.py:166-167): two single-operand products that need the user projection only."""
-        ui, iu = opset
-        with self._t("spmm_fwd"):
-            iu.apply([(self.P_usr, self.prof_i, None, False)])
-            ui.apply([(self.prof_i, self.prof_u, None, False)])
-
-    def _prof_bwd(self, opset):
-        """Gprof_i += ui^T Gprof_u ; GP_usr = iu^T Gprof_i  (the transposes of `_prof_fwd`)."""
-        uiT, iuT = opset
-        with self._t("spmm_bwd"):
-            uiT.apply([(self.Gprof_u, self.Gprof_i, self.Gprof_i, False)])
-            iuT.apply([(self.Gprof_i, self.GP_usr, None, False)])
 
     def _fuse_fwd(self):
         c = self.cfg
@@ -270,13 +254,12 @@ class HotPath:
             ops.fuse_bwd(self.gI, L + 1, self.dIl, si, coefs, dsi, True)
             self._join()
 
-    def _chain_bwd(self, gp_usr_direct=None, gpi_direct=None, with_feats=None, with_ids=True, opset=None, with_prof=True):
-        """with_feats=False: the ID chain only; with_ids=False: the side-feature operands only; with_prof=False: without the user-profile
-        operands (`_prof_bwd`); opset: (uiT, iuT) to launch through."""
+    def _chain_bwd(self, gp_usr_direct=None, gpi_direct=None, with_feats=None, with_ids=True, opset=None):
+        """with_feats=False: the ID chain only; with_ids=False: the side-feature operands only; opset: (uiT, iuT) to launch through."""
         L, S = self.L, self.S
         wf = self.has_feats if with_feats is None else with_feats
         uiT, iuT = (self.uiT, self.iuT) if opset is None else opset
-        if wf and with_prof:
+        if wf:
             # prof_u = ui . prof_i  ->  Gprof_i += ui^T Gprof_u
             with self._t("spmm_bwd"):
                 uiT.apply([(self.Gprof_u, self.Gprof_i, self.Gprof_i, False)])
@@ -296,8 +279,7 @@ class HotPath:
                 segs.append((src, self.bufU, self.dUl, False))
             if wf and l == L:
                 segs += [(self.blk(self.GFi, s), self.blk(self.GFu, s), self.blk(self.GFu, s), False) for s in range(S)]
-                if with_prof:
-                    segs.append((self.Gprof_i, self.GP_usr, gp_usr_direct, False))
+                segs.append((self.Gprof_i, self.GP_usr, gp_usr_direct, False))
             with self._t("spmm_bwd"):
                 iuT.apply(segs)
             # U_l = [softmax] ui . I_{l-1}
@@ -390,11 +372,10 @@ class HotPath:
             raise RuntimeError("attach an optimizer with set_optimizer() first")
         split = self.has_feats and self.timer is None and (self.branches or self.force_split)
         if split:
-            # Three independent strands per direction, each through operators with their own long-row scratch:
-            #   lane 0  the ID layers (no dependence on the projections), then the first touch of the gradient buffers
-            #   lane 2  the user-profile operand (needs the user projection only): two single-operand products
-            #   main    projections, the S side-feature operands
-            ids, pro = self._opset(0), self._opset(1)
+            # the ID layers do not depend on the projections: they run as a branch (through operators with their own long-row scratch)
+            # beside the projection kernel and the side-feature products; the first touch of the gradient buffers follows on the branch.
+            # (Giving the two single-operand user-profile products a lane of their own was measured: no gain, removed.)
+            ids = self._opset(0)
             if getattr(self, "_ev_ids", None) is None and self.branches:
                 self._ev_ids = torch.cuda.Event()
 
@@ -405,9 +386,7 @@ class HotPath:
 
             self._fork(id_layers, lane=0)
             self._proj_fwd()
-            self._fork(lambda: self._prof_fwd(pro[:2]), lane=2)
-            self._prop_fwd(with_ids=False, with_prof=False, after_sides=lambda: self._fork(self._grad_init, lane=0))
-            self._join(lanes=(2,))
+            self._prop_fwd(with_ids=False, after_sides=lambda: self._fork(self._grad_init, lane=0))
             if self.branches:
                 torch.cuda.current_stream().wait_event(self._ev_ids)         # the item-side fusion below reads Il; grad_init may still run
         else:
@@ -419,9 +398,7 @@ class HotPath:
         if split:
             self._fuse_bwd()
             self._fork(lambda: self._chain_bwd(with_feats=False, opset=ids[2:]), lane=0)    # ID chain
-            self._fork(lambda: self._prof_bwd(pro[2:]), lane=2)                              # user-profile operand
-            self._chain_bwd(with_ids=False, with_prof=False)                                 # S side-feature operands
-            self._join(lanes=(2,))
+            self._chain_bwd(with_ids=False)                                                  # side-feature operands
             self._wgrad()
             self._join()
         else:
