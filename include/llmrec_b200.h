@@ -144,8 +144,12 @@ typedef struct {
 int llmrec_proj_fwd_group_f32(const llmrec_proj_fwd_problem* probs_host, int32_t n_prob, int32_t d, int32_t mode,
                               llmrec_stream_t stream);
 int llmrec_proj_wgrad_group_f32(const llmrec_proj_wgrad_problem* probs_host, int32_t n_prob, int32_t d, int32_t mode,
-                                float* scratch /* zero-initialised ONCE by the caller: its last words are a ticket the kernels leave at zero */,
+                                float* scratch /* zero-initialised ONCE by the caller: its FIRST word is a ticket the kernels leave at zero */,
                                 int64_t scratch_elems, llmrec_stream_t stream);
+/* Stream note: when any problem has db != NULL, the bias column sums (they read dY only) are enqueued on a library-owned side
+ * stream forked from `stream` with an event and joined back into it before the call returns, so they overlap the persistent
+ * weight-gradient kernel; inside a stream capture this becomes a parallel graph branch.  One side stream + two events per device,
+ * created on first use (the only objects the library ever creates); LLMREC_BRANCHES=0 keeps everything on `stream`. */
 int64_t llmrec_proj_wgrad_group_scratch(const llmrec_proj_wgrad_problem* probs_host, int32_t n_prob, int32_t d, int32_t mode);
 
 /* ---------------------------------------------------------------------------------------------
