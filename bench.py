@@ -279,7 +279,6 @@ def run_workload(name, a, K, W, min_seconds, with_families=True, hoist=False, ex
 def parity_leg(a, side):
     """A fresh Trainer (same seed -> same init, asserted by the golden tests) trains on the batches the CPU oracle trained on,
     then both rank the same test users: losses, Recall@20 / NDCG@20 (north_star: within 1e-4) and the top-50 lists."""
-    import numpy as np
     import torch
     from llmrec_b200.utility import batch_test
     tr, gen, args = make_trainer(a.workload, a)
